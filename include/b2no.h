@@ -1,0 +1,148 @@
+/*
+ * b2no -- B200-native Fourier-neural-operator hot path (C ABI).
+ *
+ * Drop-in boundary for the SpectralConv hot path of neuraloperator/pde-policylearning.  The reference is
+ * pure Python/PyTorch: it has no FFI of its own, its "operator interface" for this path is the three
+ * nn.Module.forward() methods below plus the autograd backward PyTorch derives for them.  Each entry point
+ * cites the reference lines it replaces; INTEGRATION.md shows the ctypes stub a reference maintainer adds.
+ *
+ *   neuralop/models/spectral_convolution.py:303-347   FactorizedSpectralConv.forward      (a1)
+ *   neuralop/models/fno_block.py:123-170              FNOBlocks.forward (skip + act)      (a3)
+ *   neuralop/models/tfno.py:11-38                     Lifting / Projection                (a3)
+ *   neuralop/models/rno.py:60-77,224-228,254-260      SpectralConv2d / FourierLayer2d / RNO_cell (a4,a5)
+ *   libs/models/pino_models/basics.py:114-143         SpectralConv3d.forward              (a6)
+ *   libs/models/pino_models/pinobserver.py:212-232    pointwise head / tail               (a7)
+ *   libs/utilities3.py:323-334                        LpLoss.rel                          (a9)
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; buffers are owned by the caller
+ *     (PyTorch); the library allocates only the per-plan twiddle tables.
+ *   - `stream` is a cudaStream_t passed as void*; no entry point synchronises the device; all are
+ *     CUDA-graph capturable except b2no_plan_create/destroy.
+ *   - return value: 0 = ok, negative = bad argument / unsupported shape (B2NO_E_*), positive = cudaError_t.
+ *   - real tensors are contiguous fp32 (batch, channel, *grid); spectra are complex64 interleaved
+ *     (re,im) laid out (batch*channel, K_1, ..., K_d) over the KEPT modes only.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point returns an error.
+ */
+#ifndef B2NO_H
+#define B2NO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2NO_MAX_DIM 3
+#define B2NO_ABI_VERSION 1
+
+enum { B2NO_NORM_BACKWARD = 0, B2NO_NORM_FORWARD = 1, B2NO_NORM_ORTHO = 2 };
+enum { B2NO_ACT_NONE = 0, B2NO_ACT_GELU = 1, B2NO_ACT_RELU = 2, B2NO_ACT_SIGMOID = 3, B2NO_ACT_SELU = 4,
+       B2NO_ACT_TANH = 5 };
+enum { B2NO_E_ARG = -1, B2NO_E_UNSUPPORTED = -2, B2NO_E_NODEVICE = -3 };
+
+/* Geometry of one truncated spectral convolution (mirrors oracle/closed_form.py::SpecGeom).
+ *   nin  : physical input grid                      (x.shape[2:])
+ *   nfft : forward transform lengths                (== nin, except rno.py:66-67 forces (n, n))
+ *   nout : output grid                              (== nfft, except output_scaling_factor,
+ *                                                    spectral_convolution.py:339-342)
+ *   half : kept modes per dim; dims 0..ndim-2 keep rows [0,h) U [N-h,N), the last dim keeps [0,h)
+ */
+typedef struct {
+  int32_t ndim;
+  int32_t nin[B2NO_MAX_DIM];
+  int32_t nfft[B2NO_MAX_DIM];
+  int32_t nout[B2NO_MAX_DIM];
+  int32_t half[B2NO_MAX_DIM];
+  int32_t norm;
+} b2no_geom;
+
+typedef struct b2no_plan b2no_plan;
+
+/* Complex spectral weights as the reference stores them: one tensor per corner, each (Ci, Co, h_1..h_d)
+ * complex64 interleaved -- tltorch ComplexDense (spectral_convolution.py:259-266), rno.py:43-46 real pairs
+ * and basics.py:109-112 cfloat Parameters all share this memory layout.  Corner order is canonical:
+ * index = sum_j highbit_j * 2^(ndim-2-j) == itertools.product order of spectral_convolution.py:330-337.
+ * Strides are in complex elements so incremental_n_modes slices (spectral_convolution.py:276-301) work. */
+typedef struct {
+  const float* corner[4];
+  int64_t stride_i, stride_o;
+  int64_t stride_k[B2NO_MAX_DIM];
+} b2no_weights;
+
+/* Fused epilogue of the inverse transform:
+ *   z = irfft(Yh) + bias[o] + sum_i pw_w[o,i] * pw_x[b,i,.] + sum_i pw2_w[o,i] * pw2_x[b,i,.] + add[b,o,.]
+ *   y = act(z) * (mul ? mul[b,o,.] : 1)
+ * (fno_block.py:131,142-150; rno.py:224-228,254-258; pinobserver.py:222-226).  pw_w is (Co, Ci) row-major,
+ * or (Ci, Co) when pw_transposed (the dx pass of the 1x1 conv).  preact, when non-NULL, receives z. */
+typedef struct {
+  const float* bias;
+  const float* pw_w;  const float* pw_x;  int32_t pw_ci;  int32_t pw_transposed;
+  const float* pw2_w; const float* pw2_x; int32_t pw2_ci; int32_t pw2_transposed;
+  const float* add;
+  const float* mul;
+  float* preact;
+  int32_t act;
+} b2no_epilogue;
+
+int b2no_version(void);
+const char* b2no_error_string(int code);
+int b2no_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes);
+
+/* ---- plans ------------------------------------------------------------------------------------- */
+int b2no_plan_create(const b2no_geom* geom, b2no_plan** out);
+int b2no_plan_destroy(b2no_plan* plan);
+/* kept modes per dim (K_j) */
+int b2no_plan_kept(const b2no_plan* plan, int32_t kept[B2NO_MAX_DIM]);
+/* floats of scratch needed by dft_forward / dft_inverse for `bc` (batch*channel) images */
+int64_t b2no_plan_workspace_floats(const b2no_plan* plan, int64_t bc);
+
+/* ---- truncated transforms ---------------------------------------------------------------------- */
+/* which = 0: Xh = s_f * DFT_trunc(x)            x on the nin grid    (rfftn + slicing)
+ * which = 1: gYh = adjoint of the inverse       gy on the nout grid  (backward of irfftn) */
+int b2no_dft_forward(const b2no_plan* plan, int which, const float* x, float* spec, float* work,
+                     int64_t bc, void* stream);
+/* which = 0: y  = s_i * Re(IDFT_trunc(Yh)) on the nout grid, fused epilogue       (irfftn + bias ...)
+ * which = 1: dx = adjoint of the forward on the nin grid, fused epilogue           (backward of rfftn)
+ * spec may be NULL (pure pointwise op: y = act(bias + pw + add)); then `pixels` is the flattened grid. */
+int b2no_dft_inverse(const b2no_plan* plan, int which, const float* spec, float* y, float* work,
+                     int batch, int channels, int64_t pixels, const b2no_epilogue* epi, void* stream);
+
+/* ---- per-mode channel mixing ------------------------------------------------------------------- */
+/* mode 0: Yh[b,o,k]  (+)= sum_i Xh[b,i,k]  * W[i,o,k]          (the einsum, spectral_convolution.py:31-36)
+ * mode 1: gXh[b,i,k] (+)= sum_o gYh[b,o,k] * conj(W[i,o,k])    (its input adjoint) */
+int b2no_mix(const b2no_plan* plan, int mode, const float* in, const b2no_weights* w, float* out,
+             int batch, int ci, int co, int accumulate, void* stream);
+/* dW[i,o,k] (+)= sum_b conj(Xh[b,i,k]) * gYh[b,o,k]  written in the reference's corner layout */
+int b2no_mix_dw(const b2no_plan* plan, const float* xh, const float* gyh, const b2no_weights* dw,
+                int batch, int ci, int co, int accumulate, void* stream);
+
+/* ---- pointwise kernels -------------------------------------------------------------------------- */
+/* gz = gy * act'(z)  (elementwise, n floats) */
+int b2no_act_bwd(const float* gy, const float* z, float* gz, int64_t n, int act, void* stream);
+/* dW[o,i] = sum_{b,p} g[b,o,p] x[b,i,p] ; db[o] = sum_{b,p} g[b,o,p] (db may be NULL).
+ * partial: scratch of b2no_pw_wgrad_scratch_floats(ci,co) floats. */
+int64_t b2no_pw_wgrad_scratch_floats(int ci, int co);
+int b2no_pw_wgrad(const float* g, const float* x, float* dw, float* db, float* partial, int batch, int ci,
+                  int co, int64_t pixels, void* stream);
+/* fused projection head (tfno.py:34-38; pinobserver.py:230-232 after folding MultiplicativeNet):
+ *   out[b,p] = b2 + sum_j w2[j] * gelu( b1[(b),j] + sum_i w1[j,i] x[b,i,p] )      (out_channels == 1)
+ * b1 is (hidden) or, when b1_per_sample, (batch, hidden). */
+int b2no_mlp_head_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                      float* out, int batch, int ci, int hidden, int64_t pixels, int b1_per_sample,
+                      int act, void* stream);
+/* RNO gate (rno.py:259): h_next = (1 - z) * h + z2 * hhat, and its backward */
+int b2no_rno_gate_fwd(const float* z, const float* z2, const float* hhat, const float* h, float* out,
+                      int64_t n, void* stream);
+int b2no_rno_gate_bwd(const float* g, const float* z, const float* z2, const float* hhat, const float* h,
+                      float* gz, float* gz2, float* ghhat, float* gh, int64_t n, void* stream);
+/* LpLoss.rel, p=2 (utilities3.py:323-334): per-sample sums -> sums[b] = (||x-y||^2, ||y||^2) */
+int b2no_rel_l2_sums(const float* x, const float* y, float* sums, int batch, int64_t n_per_sample, void* stream);
+/* dx = coef[b] * (x - y)  with coef[b] precomputed by the host from sums (and the upstream gradient) */
+int b2no_rel_l2_bwd(const float* x, const float* y, const float* coef, float* dx, int batch,
+                    int64_t n_per_sample, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2NO_H */

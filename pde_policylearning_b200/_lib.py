@@ -1,0 +1,114 @@
+"""ctypes binding of libb2no.so (include/b2no.h).  No torch types cross this boundary: only raw device
+pointers, sizes and a cudaStream_t.  There is no fallback: if the shared library is missing or a call
+fails, we raise."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2no.so")
+CSRC = os.path.join(_HERE, "csrc")
+SOURCES = ["plan.cu", "spectral.cu", "pointwise.cu"]
+
+MAX_DIM = 3
+NORM = {"backward": 0, "forward": 1, "ortho": 2}
+ACT = {None: 0, "none": 0, "identity": 0, "gelu": 1, "relu": 2, "sigmoid": 3, "selu": 4, "tanh": 5}
+
+
+class Geom(C.Structure):
+    _fields_ = [("ndim", C.c_int32), ("nin", C.c_int32 * MAX_DIM), ("nfft", C.c_int32 * MAX_DIM),
+                ("nout", C.c_int32 * MAX_DIM), ("half", C.c_int32 * MAX_DIM), ("norm", C.c_int32)]
+
+
+class Weights(C.Structure):
+    _fields_ = [("corner", C.c_void_p * 4), ("stride_i", C.c_int64), ("stride_o", C.c_int64),
+                ("stride_k", C.c_int64 * MAX_DIM)]
+
+
+class Epilogue(C.Structure):
+    _fields_ = [("bias", C.c_void_p),
+                ("pw_w", C.c_void_p), ("pw_x", C.c_void_p), ("pw_ci", C.c_int32), ("pw_transposed", C.c_int32),
+                ("pw2_w", C.c_void_p), ("pw2_x", C.c_void_p), ("pw2_ci", C.c_int32), ("pw2_transposed", C.c_int32),
+                ("add", C.c_void_p), ("mul", C.c_void_p), ("preact", C.c_void_p), ("act", C.c_int32)]
+
+
+def nvcc_command(out_path: str = LIB_PATH):
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    return ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+            "-shared", "-Xcompiler", "-fPIC", "-o", out_path] + srcs
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into libb2no.so (in-tree, so it travels with the repo snapshot)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"),
+                                                       os.path.join(_HERE, "..", "include", "b2no.h")]
+    if not force and os.path.exists(LIB_PATH):
+        newest = max(os.path.getmtime(s) for s in srcs)
+        if os.path.getmtime(LIB_PATH) >= newest:
+            return LIB_PATH
+    cmd = nvcc_command()
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU / PyTorch fallback for the spectral-conv hot path.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    L.b2no_version.restype = i32
+    L.b2no_error_string.restype = C.c_char_p
+    L.b2no_error_string.argtypes = [i32]
+    L.b2no_device_info.argtypes = [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
+    L.b2no_plan_create.argtypes = [C.POINTER(Geom), C.POINTER(vp)]
+    L.b2no_plan_destroy.argtypes = [vp]
+    L.b2no_plan_kept.argtypes = [vp, C.POINTER(C.c_int32 * MAX_DIM)]
+    L.b2no_plan_workspace_floats.restype = i64
+    L.b2no_plan_workspace_floats.argtypes = [vp, i64]
+    L.b2no_dft_forward.argtypes = [vp, i32, vp, vp, vp, i64, vp]
+    L.b2no_dft_inverse.argtypes = [vp, i32, vp, vp, vp, i32, i32, i64, C.POINTER(Epilogue), vp]
+    L.b2no_mix.argtypes = [vp, i32, vp, C.POINTER(Weights), vp, i32, i32, i32, i32, vp]
+    L.b2no_mix_dw.argtypes = [vp, vp, vp, C.POINTER(Weights), i32, i32, i32, i32, vp]
+    L.b2no_act_bwd.argtypes = [vp, vp, vp, i64, i32, vp]
+    L.b2no_pw_wgrad_scratch_floats.restype = i64
+    L.b2no_pw_wgrad_scratch_floats.argtypes = [i32, i32]
+    L.b2no_pw_wgrad.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i64, vp]
+    L.b2no_mlp_head_fwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i64, i32, i32, vp]
+    L.b2no_rno_gate_fwd.argtypes = [vp, vp, vp, vp, vp, i64, vp]
+    L.b2no_rno_gate_bwd.argtypes = [vp] * 9 + [i64, vp]
+    L.b2no_rel_l2_sums.argtypes = [vp, vp, vp, i32, i64, vp]
+    L.b2no_rel_l2_bwd.argtypes = [vp, vp, vp, vp, i32, i64, vp]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int and name not in ("b2no_version",):
+            pass
+    _lib = L
+    return L
+
+
+EXPORTS = [
+    "b2no_version", "b2no_error_string", "b2no_device_info",
+    "b2no_plan_create", "b2no_plan_destroy", "b2no_plan_kept", "b2no_plan_workspace_floats",
+    "b2no_dft_forward", "b2no_dft_inverse", "b2no_mix", "b2no_mix_dw",
+    "b2no_act_bwd", "b2no_pw_wgrad_scratch_floats", "b2no_pw_wgrad", "b2no_mlp_head_fwd",
+    "b2no_rno_gate_fwd", "b2no_rno_gate_bwd", "b2no_rel_l2_sums", "b2no_rel_l2_bwd",
+]
+
+
+def check(code: int, what: str = "") -> None:
+    if code != 0:
+        msg = lib().b2no_error_string(int(code)).decode()
+        raise RuntimeError(f"b2no {what} failed: {msg} (code {code})")

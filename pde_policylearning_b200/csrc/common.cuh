@@ -1,0 +1,78 @@
+// Shared helpers for the b2no kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/b2no.h"
+
+#define B2NO_CHECK_CUDA(expr)                      \
+  do {                                             \
+    cudaError_t _e = (expr);                       \
+    if (_e != cudaSuccess) return (int)_e;         \
+  } while (0)
+
+#define B2NO_LAUNCH_CHECK()                        \
+  do {                                             \
+    cudaError_t _e = cudaGetLastError();           \
+    if (_e != cudaSuccess) return (int)_e;         \
+  } while (0)
+
+static inline int b2no_ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
+static inline int b2no_round_up(int a, int b) { return ((a + b - 1) / b) * b; }
+
+int b2no_sm_count();   // cached, current device
+
+struct b2no_plan {
+  b2no_geom g;
+  int K[B2NO_MAX_DIM];   // kept modes per dim
+  int device;
+  // last-dim real tables, layout [qpad][npad] (q = 2k -> re, 2k+1 -> im), zero padded
+  float* t_in;   // over the nin grid, scale s_f            (forward DFT / adjoint of forward)
+  float* t_out;  // over the nout grid, scale s_i * c(k)    (inverse DFT / adjoint of inverse)
+  int npad_in, npad_out, q2, qc, nchunk, qpad;
+  // middle dims j < ndim-1: complex matrices, row-major
+  float2* m_fwd[2];     // [nin_j][K_j]    exp(-i)
+  float2* m_inv[2];     // [K_j][nout_j]   exp(+i)
+  float2* m_adjinv[2];  // [nout_j][K_j]   conj(m_inv)^T
+  float2* m_adjfwd[2];  // [K_j][nin_j]    conj(m_fwd)^T
+  int* row_corner[2];   // [K_j] 0 = low corner, 1 = high corner
+  int* row_local[2];    // [K_j] index inside the corner's weight
+};
+
+// ---- activations (exact forms: F.gelu default is the erf form) ---------------------------------
+__device__ __forceinline__ float b2no_act(float x, int act) {
+  switch (act) {
+    case B2NO_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    case B2NO_ACT_RELU: return x > 0.f ? x : 0.f;
+    case B2NO_ACT_SIGMOID: return 1.0f / (1.0f + expf(-x));
+    case B2NO_ACT_SELU: {
+      const float scale = 1.0507009873554804934193349852946f, alpha = 1.6732632423543772848170429916717f;
+      return x > 0.f ? scale * x : scale * alpha * expm1f(x);
+    }
+    case B2NO_ACT_TANH: return tanhf(x);
+    default: return x;
+  }
+}
+
+__device__ __forceinline__ float b2no_act_grad(float x, int act) {
+  switch (act) {
+    case B2NO_ACT_GELU: {
+      const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+      const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+      return cdf + x * pdf;
+    }
+    case B2NO_ACT_RELU: return x > 0.f ? 1.f : 0.f;
+    case B2NO_ACT_SIGMOID: {
+      const float s = 1.0f / (1.0f + expf(-x));
+      return s * (1.0f - s);
+    }
+    case B2NO_ACT_SELU: {
+      const float scale = 1.0507009873554804934193349852946f, alpha = 1.6732632423543772848170429916717f;
+      return x > 0.f ? scale : scale * alpha * expf(x);
+    }
+    case B2NO_ACT_TANH: {
+      const float t = tanhf(x);
+      return 1.0f - t * t;
+    }
+    default: return 1.f;
+  }
+}

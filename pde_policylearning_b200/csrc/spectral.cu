@@ -1,0 +1,596 @@
+// Mode-restricted DFT stages, per-mode channel mixing and the fused inverse epilogue (fp32 CUDA-core
+// path).  Only the kept low modes are ever materialised: no full-size spectrum, no zero-filled out_fft.
+//
+//   k_r2c_last   x[R, N]  -> A[R, K_d]          real -> complex along the contiguous (rfft) axis
+//   k_cmat       [outer, J, inner] -> [outer, M, inner]   complex matrix along a middle axis (both directions)
+//   k_mix        Yh[b,o,k] = sum_i Xh[b,i,k] W[i,o,k]     (and the conj/transposed adjoint)
+//   k_dw         dW[i,o,k] = sum_b conj(Xh) gYh
+//   k_c2r_fused  y = act(irfft_last(Bq) + bias + W1x1 x (+ W' x') + add) * mul
+#include <string.h>
+#include "common.cuh"
+
+// =============================================================================================
+// k_r2c_last
+//   One warp transforms 8 rows at a time.  Lane l owns samples n = l + 32 j; the twiddle table sits in
+//   shared memory as [q][n] (conflict-free, one LDS feeds 8 FMAs); the 32 partial sums of every
+//   (row, q) are combined with a transposing butterfly: after 5 shuffle stages lane l holds the QC/4
+//   finished values with linear index [l*QC/4, (l+1)*QC/4) of the 8 x QC block -> coalesced store.
+// =============================================================================================
+template <int QC>
+__global__ void __launch_bounds__(256)
+k_r2c_last(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ tab,
+           long R, int N, int npad, int q2, int nchunk) {
+  extern __shared__ float s_tab[];  // [QC*nchunk][npad]
+  const int qpad = QC * nchunk;
+  for (int i = threadIdx.x; i < qpad * npad; i += blockDim.x) s_tab[i] = tab[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int npl = (N + 31) >> 5;
+  const long ngroups = (R + 7) >> 3;
+  for (long g = (long)blockIdx.x * 8 + warp; g < ngroups; g += (long)gridDim.x * 8) {
+    const long r0 = g << 3;
+    for (int c = 0; c < nchunk; c++) {
+      float v[8 * QC];
+#pragma unroll
+      for (int i = 0; i < 8 * QC; i++) v[i] = 0.f;
+      for (int j = 0; j < npl; j++) {
+        const int n = lane + (j << 5);
+        float xv[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) xv[r] = (n < N && r0 + r < R) ? __ldg(x + (r0 + r) * N + n) : 0.f;
+        const float* tq = s_tab + (size_t)(c * QC) * npad + n;
+#pragma unroll
+        for (int q = 0; q < QC; q++) {
+          const float t = tq[(size_t)q * npad];
+#pragma unroll
+          for (int r = 0; r < 8; r++) v[r * QC + q] = fmaf(xv[r], t, v[r * QC + q]);
+        }
+      }
+      // transposing butterfly over the 32 lanes
+#pragma unroll
+      for (int s = 0; s < 5; s++) {
+        const int off = 16 >> s;
+        const int half = (8 * QC) >> (s + 1);
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < half; i++) {
+          const float a = v[i], b = v[i + half];
+          const float send = upper ? a : b;
+          const float keep = upper ? b : a;
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      constexpr int PER = QC / 4;
+#pragma unroll
+      for (int i = 0; i < PER; i++) {
+        const int idx = lane * PER + i;
+        const int r = idx / QC, q = c * QC + idx % QC;
+        if (r0 + r < R && q < q2) out[(r0 + r) * q2 + q] = v[i];
+      }
+    }
+  }
+}
+
+template <int QC>
+static int launch_r2c(const float* x, float* out, const float* tab, long R, int N, int npad, int q2,
+                      int nchunk, cudaStream_t st) {
+  const size_t smem = (size_t)QC * nchunk * npad * sizeof(float);
+  if (smem > 200 * 1024) return B2NO_E_UNSUPPORTED;
+  if (smem > 48 * 1024)
+    B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_r2c_last<QC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long ngroups = (R + 7) / 8;
+  long blocks = (ngroups + 7) / 8;
+  const long cap = (long)b2no_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_r2c_last<QC><<<(unsigned)blocks, 256, smem, st>>>(x, out, tab, R, N, npad, q2, nchunk);
+  B2NO_LAUNCH_CHECK();
+  return 0;
+}
+
+static int run_r2c(const b2no_plan* p, int which, const float* x, float* out, long R, cudaStream_t st) {
+  const int d = p->g.ndim;
+  const int N = which == 0 ? p->g.nin[d - 1] : p->g.nout[d - 1];
+  const int npad = which == 0 ? p->npad_in : p->npad_out;
+  const float* tab = which == 0 ? p->t_in : p->t_out;
+  switch (p->qc) {
+    case 4: return launch_r2c<4>(x, out, tab, R, N, npad, p->q2, p->nchunk, st);
+    case 8: return launch_r2c<8>(x, out, tab, R, N, npad, p->q2, p->nchunk, st);
+    case 12: return launch_r2c<12>(x, out, tab, R, N, npad, p->q2, p->nchunk, st);
+    case 16: return launch_r2c<16>(x, out, tab, R, N, npad, p->q2, p->nchunk, st);
+  }
+  return B2NO_E_UNSUPPORTED;
+}
+
+// =============================================================================================
+// k_cmat: out[o, m, i] = sum_j in[o, j, i] * T[j, m]   (complex), one thread per (o, i) column and
+// an MT-wide tile of m in registers; T tile in shared memory (broadcast reads).
+// =============================================================================================
+template <int MT>
+__global__ void __launch_bounds__(128)
+k_cmat(const float2* __restrict__ in, float2* __restrict__ out, const float2* __restrict__ T,
+       long outer, int J, int M, int inner) {
+  extern __shared__ float2 s_T[];  // [J][MT]
+  const int m0 = blockIdx.y * MT;
+  for (int idx = threadIdx.x; idx < J * MT; idx += blockDim.x) {
+    const int j = idx / MT, mm = idx - j * MT;
+    s_T[idx] = (m0 + mm < M) ? T[(size_t)j * M + m0 + mm] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  const long total = outer * inner;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const long o = t / inner;
+    const int i = (int)(t - o * inner);
+    float2 acc[MT];
+#pragma unroll
+    for (int mm = 0; mm < MT; mm++) acc[mm] = make_float2(0.f, 0.f);
+    const float2* src = in + (o * J) * inner + i;
+#pragma unroll 4
+    for (int j = 0; j < J; j++) {
+      const float2 v = __ldg(src + (size_t)j * inner);
+      const float2* trow = s_T + j * MT;
+#pragma unroll
+      for (int mm = 0; mm < MT; mm++) {
+        const float2 w = trow[mm];
+        acc[mm].x = fmaf(v.x, w.x, fmaf(-v.y, w.y, acc[mm].x));
+        acc[mm].y = fmaf(v.x, w.y, fmaf(v.y, w.x, acc[mm].y));
+      }
+    }
+#pragma unroll
+    for (int mm = 0; mm < MT; mm++)
+      if (m0 + mm < M) out[(o * M + m0 + mm) * inner + i] = acc[mm];
+  }
+}
+
+template <int MT>
+static int launch_cmat(const float2* in, float2* out, const float2* T, long outer, int J, int M, int inner,
+                       cudaStream_t st) {
+  const size_t smem = (size_t)J * MT * sizeof(float2);
+  if (smem > 200 * 1024) return B2NO_E_UNSUPPORTED;
+  if (smem > 48 * 1024)
+    B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_cmat<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long total = outer * inner;
+  long bx = (total + 127) / 128;
+  const long cap = (long)b2no_sm_count() * 16;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, (unsigned)((M + MT - 1) / MT));
+  k_cmat<MT><<<grid, 128, smem, st>>>(in, out, T, outer, J, M, inner);
+  B2NO_LAUNCH_CHECK();
+  return 0;
+}
+
+static int run_cmat(const float2* in, float2* out, const float2* T, long outer, int J, int M, int inner,
+                    cudaStream_t st) {
+  if (M <= 4) return launch_cmat<4>(in, out, T, outer, J, M, inner, st);
+  if (M <= 8) return launch_cmat<8>(in, out, T, outer, J, M, inner, st);
+  if (M <= 12 || M == 24) return launch_cmat<12>(in, out, T, outer, J, M, inner, st);
+  return launch_cmat<16>(in, out, T, outer, J, M, inner, st);
+}
+
+// =============================================================================================
+// forward pipeline
+// =============================================================================================
+extern "C" int b2no_dft_forward(const b2no_plan* p, int which, const float* x, float* spec, float* work,
+                                int64_t bc, void* stream) {
+  if (!p || !x || !spec || bc < 1 || (which != 0 && which != 1)) return B2NO_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int d = p->g.ndim;
+  const int32_t* n = which == 0 ? p->g.nin : p->g.nout;
+  const int Kl = p->K[d - 1];
+  if (d == 1) return run_r2c(p, which, x, spec, bc, st);
+  if (!work) return B2NO_E_ARG;
+  float2* A = (float2*)work;
+  if (d == 2) {
+    int rc = run_r2c(p, which, x, (float*)A, bc * n[0], st);
+    if (rc) return rc;
+    const float2* T = which == 0 ? p->m_fwd[0] : p->m_adjinv[0];
+    return run_cmat(A, (float2*)spec, T, bc, n[0], p->K[0], Kl, st);
+  }
+  // d == 3
+  float2* Bb = A + (size_t)bc * n[0] * n[1] * Kl;
+  int rc = run_r2c(p, which, x, (float*)A, bc * n[0] * n[1], st);
+  if (rc) return rc;
+  const float2* T1 = which == 0 ? p->m_fwd[1] : p->m_adjinv[1];
+  rc = run_cmat(A, Bb, T1, bc * n[0], n[1], p->K[1], Kl, st);
+  if (rc) return rc;
+  const float2* T0 = which == 0 ? p->m_fwd[0] : p->m_adjinv[0];
+  return run_cmat(Bb, (float2*)spec, T0, bc, n[0], p->K[0], p->K[1] * Kl, st);
+}
+
+// =============================================================================================
+// k_mix / k_dw
+// =============================================================================================
+struct ModeMap {
+  const int* corner[2];
+  const int* local[2];
+  int K[3];
+  int ndim;
+};
+
+__device__ __forceinline__ void decode_mode(const ModeMap& mm, const b2no_weights& w, int k, int* corner,
+                                            long* woff) {
+  // k flattened over (K_0, .., K_{d-1}), last fastest
+  int c = 0;
+  long off = 0;
+  const int d = mm.ndim;
+  int rem = k;
+  int idx[3] = {0, 0, 0};
+  for (int j = d - 1; j >= 0; j--) {
+    idx[j] = rem % mm.K[j];
+    rem /= mm.K[j];
+  }
+  for (int j = 0; j < d - 1; j++) {
+    c = c * 2 + mm.corner[j][idx[j]];
+    off += (long)mm.local[j][idx[j]] * w.stride_k[j];
+  }
+  off += (long)idx[d - 1] * w.stride_k[d - 1];
+  *corner = c;
+  *woff = off;
+}
+
+// out[b,p,k] (+)= sum_q in[b,q,k] * Wq    with  Wq = W[q,p,k] (CONJT=false)  or  conj(W[p,q,k]) (CONJT=true)
+template <int BT, int PT, bool CONJT>
+__global__ void __launch_bounds__(128)
+k_mix(const float2* __restrict__ in, float2* __restrict__ out, b2no_weights w, ModeMap mm, int B, int Cq,
+      int Cp, int Kt, int accumulate) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= Kt) return;
+  const int b0 = blockIdx.y * BT, p0 = blockIdx.z * PT;
+  int corner;
+  long woff;
+  decode_mode(mm, w, k, &corner, &woff);
+  const float2* wbase = (const float2*)w.corner[corner] + woff;
+  float2 acc[BT][PT];
+#pragma unroll
+  for (int bb = 0; bb < BT; bb++)
+#pragma unroll
+    for (int pp = 0; pp < PT; pp++) acc[bb][pp] = make_float2(0.f, 0.f);
+  for (int q = 0; q < Cq; q++) {
+    float2 xin[BT], wv[PT];
+#pragma unroll
+    for (int bb = 0; bb < BT; bb++)
+      xin[bb] = (b0 + bb < B) ? __ldg(in + ((size_t)(b0 + bb) * Cq + q) * Kt + k) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int pp = 0; pp < PT; pp++) {
+      float2 t = make_float2(0.f, 0.f);
+      if (p0 + pp < Cp) {
+        const long off = CONJT ? ((long)(p0 + pp) * w.stride_i + (long)q * w.stride_o)
+                               : ((long)q * w.stride_i + (long)(p0 + pp) * w.stride_o);
+        t = __ldg(wbase + off);
+        if (CONJT) t.y = -t.y;
+      }
+      wv[pp] = t;
+    }
+#pragma unroll
+    for (int bb = 0; bb < BT; bb++)
+#pragma unroll
+      for (int pp = 0; pp < PT; pp++) {
+        acc[bb][pp].x = fmaf(xin[bb].x, wv[pp].x, fmaf(-xin[bb].y, wv[pp].y, acc[bb][pp].x));
+        acc[bb][pp].y = fmaf(xin[bb].x, wv[pp].y, fmaf(xin[bb].y, wv[pp].x, acc[bb][pp].y));
+      }
+  }
+#pragma unroll
+  for (int bb = 0; bb < BT; bb++)
+#pragma unroll
+    for (int pp = 0; pp < PT; pp++)
+      if (b0 + bb < B && p0 + pp < Cp) {
+        float2* dst = out + ((size_t)(b0 + bb) * Cp + p0 + pp) * Kt + k;
+        float2 r = acc[bb][pp];
+        if (accumulate) { const float2 old = *dst; r.x += old.x; r.y += old.y; }
+        *dst = r;
+      }
+}
+
+static ModeMap make_mode_map(const b2no_plan* p) {
+  ModeMap mm;
+  mm.ndim = p->g.ndim;
+  for (int j = 0; j < 3; j++) mm.K[j] = j < p->g.ndim ? p->K[j] : 1;
+  for (int j = 0; j < 2; j++) { mm.corner[j] = p->row_corner[j]; mm.local[j] = p->row_local[j]; }
+  return mm;
+}
+
+static int total_modes(const b2no_plan* p) {
+  int kt = 1;
+  for (int j = 0; j < p->g.ndim; j++) kt *= p->K[j];
+  return kt;
+}
+
+extern "C" int b2no_mix(const b2no_plan* p, int mode, const float* in, const b2no_weights* w, float* out,
+                        int batch, int ci, int co, int accumulate, void* stream) {
+  if (!p || !in || !w || !out || batch < 1 || ci < 1 || co < 1 || (mode != 0 && mode != 1)) return B2NO_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Kt = total_modes(p);
+  const ModeMap mm = make_mode_map(p);
+  const int Cq = mode == 0 ? ci : co, Cp = mode == 0 ? co : ci;
+  const int threads = Kt >= 128 ? 128 : (Kt >= 64 ? 64 : 32);
+  constexpr int BT = 4, PT = 4;
+  dim3 grid((unsigned)b2no_ceil_div(Kt, threads), (unsigned)b2no_ceil_div(batch, BT), (unsigned)b2no_ceil_div(Cp, PT));
+  if (grid.y > 65535 || grid.z > 65535) return B2NO_E_UNSUPPORTED;
+  if (mode == 0)
+    k_mix<BT, PT, false><<<grid, threads, 0, st>>>((const float2*)in, (float2*)out, *w, mm, batch, Cq, Cp, Kt, accumulate);
+  else
+    k_mix<BT, PT, true><<<grid, threads, 0, st>>>((const float2*)in, (float2*)out, *w, mm, batch, Cq, Cp, Kt, accumulate);
+  B2NO_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int IT, int OT>
+__global__ void __launch_bounds__(128)
+k_dw(const float2* __restrict__ xh, const float2* __restrict__ gyh, b2no_weights w, ModeMap mm, int B, int Ci,
+     int Co, int Kt, int accumulate) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= Kt) return;
+  const int i0 = blockIdx.y * IT, o0 = blockIdx.z * OT;
+  int corner;
+  long woff;
+  decode_mode(mm, w, k, &corner, &woff);
+  float2 acc[IT][OT];
+#pragma unroll
+  for (int ii = 0; ii < IT; ii++)
+#pragma unroll
+    for (int oo = 0; oo < OT; oo++) acc[ii][oo] = make_float2(0.f, 0.f);
+  for (int b = 0; b < B; b++) {
+    float2 xi[IT], go[OT];
+#pragma unroll
+    for (int ii = 0; ii < IT; ii++)
+      xi[ii] = (i0 + ii < Ci) ? __ldg(xh + ((size_t)b * Ci + i0 + ii) * Kt + k) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int oo = 0; oo < OT; oo++)
+      go[oo] = (o0 + oo < Co) ? __ldg(gyh + ((size_t)b * Co + o0 + oo) * Kt + k) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int ii = 0; ii < IT; ii++)
+#pragma unroll
+      for (int oo = 0; oo < OT; oo++) {
+        // conj(xi) * go
+        acc[ii][oo].x = fmaf(xi[ii].x, go[oo].x, fmaf(xi[ii].y, go[oo].y, acc[ii][oo].x));
+        acc[ii][oo].y = fmaf(xi[ii].x, go[oo].y, fmaf(-xi[ii].y, go[oo].x, acc[ii][oo].y));
+      }
+  }
+  float2* wbase = (float2*)w.corner[corner] + woff;
+#pragma unroll
+  for (int ii = 0; ii < IT; ii++)
+#pragma unroll
+    for (int oo = 0; oo < OT; oo++)
+      if (i0 + ii < Ci && o0 + oo < Co) {
+        float2* dst = wbase + (long)(i0 + ii) * w.stride_i + (long)(o0 + oo) * w.stride_o;
+        float2 r = acc[ii][oo];
+        if (accumulate) { const float2 old = *dst; r.x += old.x; r.y += old.y; }
+        *dst = r;
+      }
+}
+
+extern "C" int b2no_mix_dw(const b2no_plan* p, const float* xh, const float* gyh, const b2no_weights* dw,
+                           int batch, int ci, int co, int accumulate, void* stream) {
+  if (!p || !xh || !gyh || !dw || batch < 1 || ci < 1 || co < 1) return B2NO_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Kt = total_modes(p);
+  const ModeMap mm = make_mode_map(p);
+  const int threads = Kt >= 128 ? 128 : (Kt >= 64 ? 64 : 32);
+  constexpr int IT = 4, OT = 4;
+  dim3 grid((unsigned)b2no_ceil_div(Kt, threads), (unsigned)b2no_ceil_div(ci, IT), (unsigned)b2no_ceil_div(co, OT));
+  if (grid.y > 65535 || grid.z > 65535) return B2NO_E_UNSUPPORTED;
+  k_dw<IT, OT><<<grid, threads, 0, st>>>((const float2*)xh, (const float2*)gyh, *dw, mm, batch, ci, co, Kt, accumulate);
+  B2NO_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================
+// k_c2r_fused: last inverse stage + epilogue.  One warp per (batch, row, n-chunk, o-tile) item; lane l
+// owns n = nbase + l + 32 j.  The inverse table [q][n] and the (transposed, zero-padded) 1x1 weights sit
+// in shared memory; Bq values are warp-uniform loads.
+// =============================================================================================
+struct EpiDev {
+  const float* bias;
+  const float* pw_w; const float* pw_x; int pw_ci; int pw_t;
+  const float* pw2_w; const float* pw2_x; int pw2_ci; int pw2_t;
+  const float* add;
+  const float* mul;
+  float* preact;
+  int act;
+};
+
+template <int NPT, int OT>
+__global__ void __launch_bounds__(256)
+k_c2r_fused(const float2* __restrict__ spec, float* __restrict__ y, const float* __restrict__ tab, EpiDev e,
+            int B, int Co, long RPI, int N, long P, int Kd, int npad) {
+  extern __shared__ float smem[];
+  const int n_ot = (Co + OT - 1) / OT;
+  const int copad = n_ot * OT;
+  const int q2 = spec ? 2 * Kd : 0;
+  float* s_tab = smem;                            // [q2][npad]
+  float* s_w1 = s_tab + (size_t)q2 * npad;        // [ci1][copad]
+  float* s_w2 = s_w1 + (size_t)e.pw_ci * copad;   // [ci2][copad]
+  for (int i = threadIdx.x; i < q2 * npad; i += blockDim.x) s_tab[i] = tab[i];
+  for (int i = threadIdx.x; i < e.pw_ci * copad; i += blockDim.x) {
+    const int ci = i / copad, o = i - ci * copad;
+    float v = 0.f;
+    if (o < Co) v = e.pw_t ? e.pw_w[(size_t)ci * Co + o] : e.pw_w[(size_t)o * e.pw_ci + ci];
+    s_w1[i] = v;
+  }
+  for (int i = threadIdx.x; i < e.pw2_ci * copad; i += blockDim.x) {
+    const int ci = i / copad, o = i - ci * copad;
+    float v = 0.f;
+    if (o < Co) v = e.pw2_t ? e.pw2_w[(size_t)ci * Co + o] : e.pw2_w[(size_t)o * e.pw2_ci + ci];
+    s_w2[i] = v;
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_nc = (N + 32 * NPT - 1) / (32 * NPT);
+  const long n_items = (long)B * RPI * n_nc * n_ot;
+  for (long item = (long)blockIdx.x * 8 + warp; item < n_items; item += (long)gridDim.x * 8) {
+    const int ot = (int)(item % n_ot);
+    long t = item / n_ot;
+    const int nc = (int)(t % n_nc);
+    t /= n_nc;
+    const long r = t % RPI;
+    const int b = (int)(t / RPI);
+    const int o0 = ot * OT;
+    const int nbase = nc * 32 * NPT;
+
+    float acc[OT][NPT];
+#pragma unroll
+    for (int oo = 0; oo < OT; oo++)
+#pragma unroll
+      for (int j = 0; j < NPT; j++) acc[oo][j] = 0.f;
+
+    if (spec) {
+      const float2* sp = spec + (((size_t)b * Co + o0) * RPI + r) * Kd;
+      const size_t ostride = (size_t)RPI * Kd;
+      for (int k = 0; k < Kd; k++) {
+        float tr[NPT], ti[NPT];
+#pragma unroll
+        for (int j = 0; j < NPT; j++) {
+          const int n = nbase + lane + 32 * j;  // < npad by construction (npad multiple of 128)
+          tr[j] = s_tab[(size_t)(2 * k) * npad + n];
+          ti[j] = s_tab[(size_t)(2 * k + 1) * npad + n];
+        }
+#pragma unroll
+        for (int oo = 0; oo < OT; oo++) {
+          if (o0 + oo < Co) {
+            const float2 v = __ldg(sp + oo * ostride + k);
+#pragma unroll
+            for (int j = 0; j < NPT; j++) acc[oo][j] = fmaf(v.x, tr[j], fmaf(v.y, ti[j], acc[oo][j]));
+          }
+        }
+      }
+    }
+    bool valid[NPT];
+    long pix[NPT];
+#pragma unroll
+    for (int j = 0; j < NPT; j++) {
+      const int n = nbase + lane + 32 * j;
+      pix[j] = r * N + n;
+      valid[j] = (n < N) && (pix[j] < P);
+    }
+    if (e.pw_ci > 0) {
+      const float* xb = e.pw_x + (size_t)b * e.pw_ci * P;
+      for (int i = 0; i < e.pw_ci; i++) {
+        float xv[NPT];
+#pragma unroll
+        for (int j = 0; j < NPT; j++) xv[j] = valid[j] ? __ldg(xb + (size_t)i * P + pix[j]) : 0.f;
+        const float* wr = s_w1 + (size_t)i * copad + o0;
+#pragma unroll
+        for (int oo = 0; oo < OT; oo++) {
+          const float wv = wr[oo];
+#pragma unroll
+          for (int j = 0; j < NPT; j++) acc[oo][j] = fmaf(wv, xv[j], acc[oo][j]);
+        }
+      }
+    }
+    if (e.pw2_ci > 0) {
+      const float* xb = e.pw2_x + (size_t)b * e.pw2_ci * P;
+      for (int i = 0; i < e.pw2_ci; i++) {
+        float xv[NPT];
+#pragma unroll
+        for (int j = 0; j < NPT; j++) xv[j] = valid[j] ? __ldg(xb + (size_t)i * P + pix[j]) : 0.f;
+        const float* wr = s_w2 + (size_t)i * copad + o0;
+#pragma unroll
+        for (int oo = 0; oo < OT; oo++) {
+          const float wv = wr[oo];
+#pragma unroll
+          for (int j = 0; j < NPT; j++) acc[oo][j] = fmaf(wv, xv[j], acc[oo][j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int oo = 0; oo < OT; oo++) {
+      const int o = o0 + oo;
+      if (o < Co) {
+        const float bv = e.bias ? __ldg(e.bias + o) : 0.f;
+#pragma unroll
+        for (int j = 0; j < NPT; j++) {
+          if (valid[j]) {
+            const size_t idx = ((size_t)b * Co + o) * P + pix[j];
+            float z = acc[oo][j] + bv;
+            if (e.add) z += __ldg(e.add + idx);
+            if (e.preact) e.preact[idx] = z;
+            float v = b2no_act(z, e.act);
+            if (e.mul) v *= __ldg(e.mul + idx);
+            y[idx] = v;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int NPT, int OT>
+static int launch_c2r(const float2* spec, float* y, const float* tab, const EpiDev& e, int B, int Co, long RPI,
+                      int N, long P, int Kd, int npad, cudaStream_t st) {
+  const int n_ot = (Co + OT - 1) / OT;
+  const int copad = n_ot * OT;
+  const size_t smem = ((size_t)(spec ? 2 * Kd : 0) * npad + (size_t)(e.pw_ci + e.pw2_ci) * copad) * sizeof(float);
+  if (smem > 200 * 1024) return B2NO_E_UNSUPPORTED;
+  if (smem > 48 * 1024)
+    B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_c2r_fused<NPT, OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int n_nc = (N + 32 * NPT - 1) / (32 * NPT);
+  const long n_items = (long)B * RPI * n_nc * n_ot;
+  long blocks = (n_items + 7) / 8;
+  const long cap = (long)b2no_sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_c2r_fused<NPT, OT><<<(unsigned)blocks, 256, smem, st>>>(spec, y, tab, e, B, Co, RPI, N, P, Kd, npad);
+  B2NO_LAUNCH_CHECK();
+  return 0;
+}
+
+static int run_c2r(const float2* spec, float* y, const float* tab, const EpiDev& e, int B, int Co, long RPI, int N,
+                   long P, int Kd, int npad, cudaStream_t st) {
+  constexpr int OT = 16;
+  if (N <= 32) return launch_c2r<1, OT>(spec, y, tab, e, B, Co, RPI, N, P, Kd, npad, st);
+  if (N <= 64) return launch_c2r<2, OT>(spec, y, tab, e, B, Co, RPI, N, P, Kd, npad, st);
+  if (N <= 96) return launch_c2r<3, OT>(spec, y, tab, e, B, Co, RPI, N, P, Kd, npad, st);
+  return launch_c2r<4, OT>(spec, y, tab, e, B, Co, RPI, N, P, Kd, npad, st);
+}
+
+extern "C" int b2no_dft_inverse(const b2no_plan* p, int which, const float* spec, float* y, float* work,
+                                int batch, int channels, int64_t pixels, const b2no_epilogue* epi, void* stream) {
+  if (!y || batch < 1 || channels < 1 || (which != 0 && which != 1)) return B2NO_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  EpiDev e;
+  memset(&e, 0, sizeof(e));
+  if (epi) {
+    e.bias = epi->bias;
+    e.pw_w = epi->pw_w; e.pw_x = epi->pw_x; e.pw_ci = (epi->pw_w && epi->pw_x) ? epi->pw_ci : 0; e.pw_t = epi->pw_transposed;
+    e.pw2_w = epi->pw2_w; e.pw2_x = epi->pw2_x; e.pw2_ci = (epi->pw2_w && epi->pw2_x) ? epi->pw2_ci : 0; e.pw2_t = epi->pw2_transposed;
+    e.add = epi->add; e.mul = epi->mul; e.preact = epi->preact; e.act = epi->act;
+    if (e.pw_ci < 0 || e.pw2_ci < 0) return B2NO_E_ARG;
+  }
+  if (!spec) {
+    // pure pointwise op on a flattened grid
+    if (pixels < 1) return B2NO_E_ARG;
+    const int N = 128;
+    const long RPI = (pixels + N - 1) / N;
+    return run_c2r(nullptr, y, nullptr, e, batch, channels, RPI, N, pixels, 0, 128, st);
+  }
+  if (!p) return B2NO_E_ARG;
+  const int d = p->g.ndim;
+  const int32_t* n = which == 0 ? p->g.nout : p->g.nin;
+  const int Kl = p->K[d - 1];
+  const float* tab = which == 0 ? p->t_out : p->t_in;
+  const int npad = which == 0 ? p->npad_out : p->npad_in;
+  const long bc = (long)batch * channels;
+  long P = 1;
+  for (int j = 0; j < d; j++) P *= n[j];
+  if (pixels > 0 && pixels != P) return B2NO_E_ARG;
+  if (d == 1) return run_c2r((const float2*)spec, y, tab, e, batch, channels, 1, n[0], P, Kl, npad, st);
+  if (!work) return B2NO_E_ARG;
+  float2* A = (float2*)work;
+  if (d == 2) {
+    const float2* T = which == 0 ? p->m_inv[0] : p->m_adjfwd[0];
+    int rc = run_cmat((const float2*)spec, A, T, bc, p->K[0], n[0], Kl, st);
+    if (rc) return rc;
+    return run_c2r(A, y, tab, e, batch, channels, n[0], n[1], P, Kl, npad, st);
+  }
+  float2* Bb = A + (size_t)bc * n[0] * n[1] * Kl;
+  const float2* T0 = which == 0 ? p->m_inv[0] : p->m_adjfwd[0];
+  int rc = run_cmat((const float2*)spec, Bb, T0, bc, p->K[0], n[0], p->K[1] * Kl, st);
+  if (rc) return rc;
+  const float2* T1 = which == 0 ? p->m_inv[1] : p->m_adjfwd[1];
+  rc = run_cmat(Bb, A, T1, bc * n[0], p->K[1], n[1], Kl, st);
+  if (rc) return rc;
+  return run_c2r(A, y, tab, e, batch, channels, (long)n[0] * n[1], n[2], P, Kl, npad, st);
+}

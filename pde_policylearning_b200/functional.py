@@ -1,0 +1,253 @@
+"""Autograd layer over the C-ABI ops: forward and hand-derived backward of the fused blocks.
+
+The math is SURVEY.md 8a.0 (verified against the reference by oracle/closed_form.py):
+
+    Xh  = s_f DFT_trunc(x)                   Yh = sum_i Xh W            y = act(s_i IDFT_trunc(Yh) + bias + Wp x)
+    gz  = gy act'(z)                         gYh = adj_inverse(gz)      dW = sum_b conj(Xh) gYh
+    gXh = sum_o gYh conj(W)                  dx  = adj_forward(gXh) + Wp^T gz       dWp = sum gz x^T
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .ops import SpecGeom, get_plan
+
+
+def _contig(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _geom_has_overlap(geom: SpecGeom) -> bool:
+    g = geom.resolved()
+    return any(2 * g.half[j] > g.nfft[j] for j in range(g.ndim - 1))
+
+
+class SpectralBlockFn(torch.autograd.Function):
+    """y = act( spectral_conv(x; corners) + bias + pw_w @ x ) -- FNOBlocks layer (fno_block.py:131-150),
+    FourierLayer2d (rno.py:224-228), PINO layer (pinobserver.py:222-226) and, with pw_w=None, the bare
+    spectral convolutions (spectral_convolution.py:303-347, rno.py:60-77, basics.py:114-143)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, pw_w, geom: SpecGeom, act, *corners):
+        ops._require_cuda(x)
+        x = _contig(x.float())
+        plan = get_plan(geom, x.device)
+        B, ci = x.shape[:2]
+        co = corners[0].shape[1]
+        if corners[0].shape[0] != ci:
+            raise ValueError(f"input has {ci} channels, weights expect {corners[0].shape[0]}")
+        det = [c.detach() for c in corners]
+        xh = ops.dft_forward(plan, 0, x)
+        yh = ops.mix(plan, 0, xh, det, ci, co)
+        need_z = act not in (None, "none") and any(ctx.needs_input_grad)
+        grid = plan.geom.nout
+        z = torch.empty((B, co) + tuple(grid), dtype=torch.float32, device=x.device) if need_z else None
+        pw2d = None
+        if pw_w is not None:
+            if tuple(plan.geom.nout) != tuple(plan.geom.nin):
+                raise NotImplementedError("fused 1x1 skip needs matching input/output grids")
+            pw2d = _contig(pw_w.detach().reshape(pw_w.shape[0], -1).float())
+        epi = ops.make_epilogue(bias=None if bias is None else _contig(bias.detach().reshape(-1).float()),
+                                pw_w=pw2d, pw_x=x if pw2d is not None else None, preact=z, act=act)
+        y = ops.dft_inverse(plan, 0, yh, epi)
+        ctx.geom, ctx.act = geom, act
+        ctx.has_bias, ctx.has_pw = bias is not None, pw_w is not None
+        ctx.pw_shape = None if pw_w is None else tuple(pw_w.shape)
+        ctx.bias_shape = None if bias is None else tuple(bias.shape)
+        ctx.save_for_backward(x, xh, z, pw2d, *det)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, xh, z, pw2d, *det = ctx.saved_tensors
+        geom, act = ctx.geom, ctx.act
+        plan = get_plan(geom, x.device)
+        B, ci = x.shape[:2]
+        co = det[0].shape[1]
+        gy = _contig(gy.float())
+        gz = ops.act_bwd(gy, z, act) if z is not None else gy
+        need_x, need_b, need_pw = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        need_w = any(ctx.needs_input_grad[5:])
+        gyh = ops.dft_forward(plan, 1, gz)
+        dbias = dpw = dx = None
+        dcorners: List[Optional[torch.Tensor]] = [None] * len(det)
+        if need_w:
+            dcorners = ops.mix_dw(plan, xh, gyh, det, needs_zero=_geom_has_overlap(geom))
+        if need_pw:
+            dpw, db2 = ops.pw_wgrad(gz, x, need_bias=need_b)
+            dpw = dpw.reshape(ctx.pw_shape)
+            if need_b:
+                dbias = db2.reshape(ctx.bias_shape)
+        elif need_b:
+            # dbias[o] = sum_{b,n} gz = DC mode of the (scaled) truncated DFT: gYh[b,o,0..0] = s_i * sum_n gz
+            dc = gyh.reshape(B, co, -1)[:, :, 0].real.sum(dim=0) / plan.s_i
+            dbias = dc.reshape(ctx.bias_shape)
+        if need_x:
+            gxh = ops.mix(plan, 1, gyh, det, ci, co)
+            epi = ops.make_epilogue(pw_w=pw2d, pw_x=gz if pw2d is not None else None, pw_transposed=True)
+            dx = ops.dft_inverse(plan, 1, gxh, epi)
+        return (dx, dbias, dpw, None, None) + tuple(dcorners)
+
+
+def spectral_block(x, corners: Sequence[torch.Tensor], geom: SpecGeom, bias=None, pw_weight=None, act=None):
+    return SpectralBlockFn.apply(x, bias, pw_weight, geom, act, *corners)
+
+
+class PointwiseConvFn(torch.autograd.Function):
+    """y = act(W x + b), channels-first 1x1 convolution (tfno.py:11-38 Lifting / Projection convs,
+    skip_connections.py:31)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        ops._require_cuda(x)
+        x = _contig(x.float())
+        B, ci = x.shape[:2]
+        grid = tuple(x.shape[2:])
+        w2d = _contig(weight.detach().reshape(weight.shape[0], -1).float())
+        co = w2d.shape[0]
+        if w2d.shape[1] != ci:
+            raise ValueError(f"input has {ci} channels, weight expects {w2d.shape[1]}")
+        need_z = act not in (None, "none") and any(ctx.needs_input_grad)
+        z = torch.empty((B, co) + grid, dtype=torch.float32, device=x.device) if need_z else None
+        epi = ops.make_epilogue(bias=None if bias is None else _contig(bias.detach().float()), pw_w=w2d, pw_x=x,
+                                preact=z, act=act)
+        y = ops.pointwise(B, co, grid, x.device, epi)
+        ctx.act = act
+        ctx.w_shape = tuple(weight.shape)
+        ctx.save_for_backward(x, z, w2d)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, z, w2d = ctx.saved_tensors
+        gy = _contig(gy.float())
+        gz = ops.act_bwd(gy, z, ctx.act) if z is not None else gy
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            epi = ops.make_epilogue(pw_w=w2d, pw_x=gz, pw_transposed=True)
+            dx = ops.pointwise(x.shape[0], x.shape[1], tuple(x.shape[2:]), x.device, epi)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dw, db = ops.pw_wgrad(gz, x, need_bias=ctx.needs_input_grad[2])
+            dw = dw.reshape(ctx.w_shape)
+        return dx, dw, db, None
+
+
+def pointwise_conv(x, weight, bias=None, act=None):
+    return PointwiseConvFn.apply(x, weight, bias, act)
+
+
+class PointwiseConv2Fn(torch.autograd.Function):
+    """y = act(W x + W2 x2 + b): two channels-first operands on the same grid (used where a per-sample
+    scalar such as the Reynolds number enters as an extra 1-channel map, pinobserver.py:51-58)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, x2, weight2):
+        ops._require_cuda(x, x2)
+        x, x2 = _contig(x.float()), _contig(x2.float())
+        B, ci = x.shape[:2]
+        grid = tuple(x.shape[2:])
+        if tuple(x2.shape[2:]) != grid or x2.shape[0] != B:
+            raise ValueError("both operands must share batch and grid")
+        w2d = _contig(weight.detach().reshape(weight.shape[0], -1).float())
+        w2d2 = _contig(weight2.detach().reshape(weight2.shape[0], -1).float())
+        co = w2d.shape[0]
+        need_z = act not in (None, "none") and any(ctx.needs_input_grad)
+        z = torch.empty((B, co) + grid, dtype=torch.float32, device=x.device) if need_z else None
+        epi = ops.make_epilogue(bias=None if bias is None else _contig(bias.detach().float()), pw_w=w2d, pw_x=x,
+                                pw2_w=w2d2, pw2_x=x2, preact=z, act=act)
+        y = ops.pointwise(B, co, grid, x.device, epi)
+        ctx.act = act
+        ctx.w_shape, ctx.w2_shape = tuple(weight.shape), tuple(weight2.shape)
+        ctx.save_for_backward(x, x2, z, w2d, w2d2)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, x2, z, w2d, w2d2 = ctx.saved_tensors
+        gy = _contig(gy.float())
+        gz = ops.act_bwd(gy, z, ctx.act) if z is not None else gy
+        dx = dw = db = dx2 = dw2 = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.pointwise(x.shape[0], x.shape[1], tuple(x.shape[2:]), x.device,
+                               ops.make_epilogue(pw_w=w2d, pw_x=gz, pw_transposed=True))
+        if ctx.needs_input_grad[4]:
+            dx2 = ops.pointwise(x2.shape[0], x2.shape[1], tuple(x2.shape[2:]), x2.device,
+                                ops.make_epilogue(pw_w=w2d2, pw_x=gz, pw_transposed=True))
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dw, db = ops.pw_wgrad(gz, x, need_bias=ctx.needs_input_grad[2])
+            dw = dw.reshape(ctx.w_shape)
+        if ctx.needs_input_grad[5]:
+            dw2, _ = ops.pw_wgrad(gz, x2, need_bias=False)
+            dw2 = dw2.reshape(ctx.w2_shape)
+        return dx, dw, db, None, dx2, dw2
+
+
+def pointwise_conv2(x, weight, bias, act, x2, weight2):
+    return PointwiseConv2Fn.apply(x, weight, bias, act, x2, weight2)
+
+
+def mlp_head(x, w1, b1, w2, b2, act="gelu"):
+    """Projection head Ci -> hidden -> act -> 1 (tfno.py:34-38).  Without autograd the fused kernel never
+    materialises the hidden tensor; with autograd it is two pointwise convs (hidden saved for backward)."""
+    needs_grad = torch.is_grad_enabled() and any(
+        t is not None and t.requires_grad for t in (x, w1, b1, w2, b2))
+    if (not needs_grad and w2.reshape(-1, w1.shape[0]).shape[0] == 1 and x.shape[1] in (8, 16, 32, 64)
+            and (b1 is None or b1.dim() <= 2)):
+        return ops.mlp_head_fwd(_contig(x.float()), _contig(w1.reshape(w1.shape[0], -1).float()),
+                                None if b1 is None else _contig(b1.float()), _contig(w2.reshape(-1).float()),
+                                None if b2 is None else _contig(b2.float()), act)
+    h = pointwise_conv(x, w1, b1, act)
+    return pointwise_conv(h, w2, b2, None)
+
+
+class RelL2Fn(torch.autograd.Function):
+    """LpLoss.rel with p=2 (libs/utilities3.py:323-334): sum_b or mean_b of ||x_b - y_b|| / ||y_b||."""
+
+    @staticmethod
+    def forward(ctx, x, y, size_average):
+        ops._require_cuda(x, y)
+        B = x.shape[0]
+        xf, yf = _contig(x.float()).reshape(B, -1), _contig(y.float()).reshape(B, -1)
+        sums = ops.rel_l2_sums(xf, yf)
+        d, n = sums[:, 0].sqrt(), sums[:, 1].sqrt()
+        ctx.save_for_backward(xf, yf, d, n)
+        ctx.size_average = size_average
+        ctx.x_shape = tuple(x.shape)
+        r = d / n
+        return r.mean() if size_average else r.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        xf, yf, d, n = ctx.saved_tensors
+        B = xf.shape[0]
+        coef = g / (d * n)
+        if ctx.size_average:
+            coef = coef / B
+        dx = ops.rel_l2_bwd(xf, yf, _contig(coef.float()))
+        return dx.reshape(ctx.x_shape), None, None
+
+
+def rel_l2_loss(x, y, size_average=True):
+    return RelL2Fn.apply(x, y, size_average)
+
+
+class RnoGateFn(torch.autograd.Function):
+    """h_next = (1 - z) * h + z2 * hhat  (rno.py:259)."""
+
+    @staticmethod
+    def forward(ctx, z, z2, hhat, h):
+        z, z2, hhat, h = (_contig(t.float()) for t in (z, z2, hhat, h))
+        ctx.save_for_backward(z, z2, hhat, h)
+        return ops.rno_gate_fwd(z, z2, hhat, h)
+
+    @staticmethod
+    def backward(ctx, g):
+        z, z2, hhat, h = ctx.saved_tensors
+        return tuple(ops.rno_gate_bwd(_contig(g.float()), z, z2, hhat, h))
+
+
+def rno_gate(z, z2, hhat, h):
+    return RnoGateFn.apply(z, z2, hhat, h)

@@ -1,0 +1,313 @@
+"""Thin tensor-level wrappers over the C ABI (no autograd here).  PyTorch owns every buffer; the C side
+only sees device pointers, sizes and the current CUDA stream."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT, NORM, Epilogue, Geom, Weights, check
+
+
+# number of libb2no kernels launched so far (bench.py reports the per-step count as `gpu_launches`)
+LAUNCHES = [0]
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "pde_policylearning_b200: the spectral-conv hot path runs only on CUDA (sm_100a); "
+                f"got a tensor on {t.device}.  There is no CPU fallback.")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ---------------------------------------------------------------------------------------------
+# geometry / plans
+# ---------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class SpecGeom:
+    """Same fields as include/b2no.h::b2no_geom (and oracle/closed_form.py::SpecGeom)."""
+    nin: Tuple[int, ...]
+    half: Tuple[int, ...]
+    norm: str = "backward"
+    nfft: Optional[Tuple[int, ...]] = None
+    nout: Optional[Tuple[int, ...]] = None
+
+    def resolved(self) -> "SpecGeom":
+        nfft = tuple(self.nin) if self.nfft is None else tuple(self.nfft)
+        nout = nfft if self.nout is None else tuple(self.nout)
+        return SpecGeom(tuple(self.nin), tuple(self.half), self.norm, nfft, nout)
+
+    @property
+    def ndim(self):
+        return len(self.nin)
+
+    def scales(self):
+        g = self.resolved()
+        n, npr = math.prod(g.nfft), math.prod(g.nout)
+        if g.norm == "forward":
+            return 1.0 / n, 1.0
+        if g.norm == "backward":
+            return 1.0, 1.0 / npr
+        if g.norm == "ortho":
+            return 1.0 / math.sqrt(n), 1.0 / math.sqrt(npr)
+        raise ValueError(f"unknown fft norm {g.norm!r}")
+
+
+class Plan:
+    def __init__(self, geom: SpecGeom, device: torch.device):
+        g = geom.resolved()
+        if not 1 <= g.ndim <= _lib.MAX_DIM:
+            raise NotImplementedError(f"spectral conv supports 1-3 spatial dims, got {g.ndim}")
+        if g.norm not in NORM:
+            raise ValueError(f"unknown fft norm {g.norm!r}")
+        for j in range(g.ndim - 1):
+            if g.half[j] > g.nfft[j]:
+                raise ValueError("kept modes exceed the grid size")
+        cg = Geom()
+        cg.ndim = g.ndim
+        for j in range(g.ndim):
+            cg.nin[j], cg.nfft[j], cg.nout[j], cg.half[j] = g.nin[j], g.nfft[j], g.nout[j], g.half[j]
+        cg.norm = NORM[g.norm]
+        handle = C.c_void_p()
+        with torch.cuda.device(device):
+            check(_lib.lib().b2no_plan_create(C.byref(cg), C.byref(handle)), "plan_create")
+        self.handle = handle
+        self.geom = g
+        self.device = device
+        kept = (C.c_int32 * _lib.MAX_DIM)()
+        check(_lib.lib().b2no_plan_kept(handle, C.byref(kept)), "plan_kept")
+        self.kept = tuple(int(kept[j]) for j in range(g.ndim))
+        self.modes = math.prod(self.kept)
+        self.s_f, self.s_i = g.scales()
+
+    def workspace(self, bc: int) -> Optional[torch.Tensor]:
+        n = int(_lib.lib().b2no_plan_workspace_floats(self.handle, bc))
+        if n < 0:
+            check(n, "workspace")
+        if n == 0:
+            return None
+        return torch.empty(n, dtype=torch.float32, device=self.device)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.lib().b2no_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+_plans = {}
+
+
+def get_plan(geom: SpecGeom, device: torch.device) -> Plan:
+    key = (geom.resolved(), device.index if device.index is not None else torch.cuda.current_device())
+    p = _plans.get(key)
+    if p is None:
+        p = Plan(geom, torch.device("cuda", key[1]))
+        _plans[key] = p
+    return p
+
+
+# ---------------------------------------------------------------------------------------------
+# weights
+# ---------------------------------------------------------------------------------------------
+def weights_struct(corners: Sequence[torch.Tensor], ndim: int) -> Weights:
+    """corners: canonical order; each complex64 (Ci,Co,*h) or float32 real pairs (Ci,Co,*h,2)."""
+    w = Weights()
+    t0 = corners[0]
+    for i, t in enumerate(corners):
+        _require_cuda(t)
+        if t.is_complex():
+            if t.dtype != torch.complex64:
+                raise TypeError("spectral weights must be complex64")
+            strides = t.stride()
+        else:
+            if t.dtype != torch.float32 or t.shape[-1] != 2 or t.stride(-1) != 1:
+                raise TypeError("real-pair spectral weights must be float32 (..., 2) with unit last stride")
+            if any(s % 2 for s in t.stride()[:-1]):
+                raise TypeError("real-pair weight strides must be even")
+            strides = tuple(s // 2 for s in t.stride()[:-1])
+        if i == 0:
+            s0 = strides
+        elif tuple(strides) != tuple(s0) or t.shape != t0.shape:
+            raise ValueError("all corner weights must share shape and strides")
+        w.corner[i] = t.data_ptr()
+    w.stride_i, w.stride_o = s0[0], s0[1]
+    for j in range(ndim):
+        w.stride_k[j] = s0[2 + j]
+    return w
+
+
+# ---------------------------------------------------------------------------------------------
+# raw ops
+# ---------------------------------------------------------------------------------------------
+def dft_forward(plan: Plan, which: int, x: torch.Tensor) -> torch.Tensor:
+    """x (B, C, *grid) fp32 contiguous -> spectrum (B, C, *kept) complex64."""
+    _require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    B, Cc = x.shape[:2]
+    grid = plan.geom.nin if which == 0 else plan.geom.nout
+    if tuple(x.shape[2:]) != tuple(grid):
+        raise ValueError(f"expected grid {tuple(grid)}, got {tuple(x.shape[2:])}")
+    spec = torch.empty((B, Cc) + plan.kept, dtype=torch.complex64, device=x.device)
+    work = plan.workspace(B * Cc)
+    check(_lib.lib().b2no_dft_forward(plan.handle, which, _ptr(x), _ptr(spec), _ptr(work), B * Cc, _stream()),
+          "dft_forward")
+    LAUNCHES[0] += plan.geom.ndim
+    return spec
+
+
+def make_epilogue(bias=None, pw_w=None, pw_x=None, pw_transposed=False, pw2_w=None, pw2_x=None,
+                  pw2_transposed=False, add=None, mul=None, preact=None, act=None) -> Epilogue:
+    e = Epilogue()
+    keep = []
+    for name, t in (("bias", bias), ("pw_w", pw_w), ("pw_x", pw_x), ("pw2_w", pw2_w), ("pw2_x", pw2_x),
+                    ("add", add), ("mul", mul), ("preact", preact)):
+        if t is not None:
+            _require_cuda(t)
+            assert t.dtype == torch.float32 and t.is_contiguous(), name
+            setattr(e, name, t.data_ptr())
+            keep.append(t)
+    if pw_w is not None:
+        e.pw_ci = pw_x.shape[1]
+        e.pw_transposed = 1 if pw_transposed else 0
+    if pw2_w is not None:
+        e.pw2_ci = pw2_x.shape[1]
+        e.pw2_transposed = 1 if pw2_transposed else 0
+    e.act = ACT[act]
+    e._keep = keep
+    return e
+
+
+def dft_inverse(plan: Plan, which: int, spec: torch.Tensor, epi: Optional[Epilogue] = None) -> torch.Tensor:
+    """spectrum (B, C, *kept) complex64 -> y (B, C, *grid) fp32, with the fused epilogue."""
+    _require_cuda(spec)
+    assert spec.dtype == torch.complex64 and spec.is_contiguous()
+    B, Cc = spec.shape[:2]
+    if tuple(spec.shape[2:]) != plan.kept:
+        raise ValueError(f"expected kept modes {plan.kept}, got {tuple(spec.shape[2:])}")
+    grid = plan.geom.nout if which == 0 else plan.geom.nin
+    y = torch.empty((B, Cc) + tuple(grid), dtype=torch.float32, device=spec.device)
+    work = plan.workspace(B * Cc)
+    check(_lib.lib().b2no_dft_inverse(plan.handle, which, _ptr(spec), _ptr(y), _ptr(work), B, Cc,
+                                      math.prod(grid), C.byref(epi) if epi is not None else None, _stream()),
+          "dft_inverse")
+    LAUNCHES[0] += plan.geom.ndim
+    return y
+
+
+def pointwise(batch: int, channels: int, grid: Tuple[int, ...], device, epi: Epilogue) -> torch.Tensor:
+    """y = act(bias + pw + pw2 + add) * mul  with no spectral term."""
+    y = torch.empty((batch, channels) + tuple(grid), dtype=torch.float32, device=device)
+    check(_lib.lib().b2no_dft_inverse(None, 0, None, _ptr(y), None, batch, channels, math.prod(grid),
+                                      C.byref(epi), _stream()), "pointwise")
+    LAUNCHES[0] += 1
+    return y
+
+
+def mix(plan: Plan, mode: int, spec: torch.Tensor, corners: Sequence[torch.Tensor], ci: int, co: int,
+        out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    _require_cuda(spec)
+    assert spec.dtype == torch.complex64 and spec.is_contiguous()
+    B = spec.shape[0]
+    cin, cout = (ci, co) if mode == 0 else (co, ci)
+    assert spec.shape[1] == cin, (spec.shape, cin)
+    if out is None:
+        out = torch.empty((B, cout) + plan.kept, dtype=torch.complex64, device=spec.device)
+        accumulate = False
+    w = weights_struct(corners, plan.geom.ndim)
+    check(_lib.lib().b2no_mix(plan.handle, mode, _ptr(spec), C.byref(w), _ptr(out), B, ci, co,
+                              1 if accumulate else 0, _stream()), "mix")
+    LAUNCHES[0] += 1
+    return out
+
+
+def mix_dw(plan: Plan, xh: torch.Tensor, gyh: torch.Tensor, like: Sequence[torch.Tensor], needs_zero: bool):
+    """Returns the list of corner gradients shaped/typed like `like`."""
+    B, ci = xh.shape[:2]
+    co = gyh.shape[1]
+    alloc = torch.zeros_like if needs_zero else torch.empty_like
+    grads = [alloc(t, memory_format=torch.contiguous_format) for t in like]
+    w = weights_struct(grads, plan.geom.ndim)
+    check(_lib.lib().b2no_mix_dw(plan.handle, _ptr(xh), _ptr(gyh), C.byref(w), B, ci, co, 0, _stream()), "mix_dw")
+    LAUNCHES[0] += 1
+    return grads
+
+
+def act_bwd(gy: torch.Tensor, z: torch.Tensor, act) -> torch.Tensor:
+    gz = torch.empty_like(gy)
+    check(_lib.lib().b2no_act_bwd(_ptr(gy), _ptr(z), _ptr(gz), gy.numel(), ACT[act], _stream()), "act_bwd")
+    LAUNCHES[0] += 1
+    return gz
+
+
+def pw_wgrad(g: torch.Tensor, x: torch.Tensor, need_bias: bool):
+    """g (B, Co, *grid), x (B, Ci, *grid) -> dW (Co, Ci), db (Co) | None."""
+    B, co = g.shape[:2]
+    ci = x.shape[1]
+    P = math.prod(g.shape[2:])
+    L = _lib.lib()
+    n = int(L.b2no_pw_wgrad_scratch_floats(ci, co))
+    partial = torch.empty(n, dtype=torch.float32, device=g.device)
+    dw = torch.empty((co, ci), dtype=torch.float32, device=g.device)
+    db = torch.empty((co,), dtype=torch.float32, device=g.device) if need_bias else None
+    check(L.b2no_pw_wgrad(_ptr(g), _ptr(x), _ptr(dw), _ptr(db), _ptr(partial), B, ci, co, P, _stream()), "pw_wgrad")
+    LAUNCHES[0] += 2
+    return dw, db
+
+
+def mlp_head_fwd(x, w1, b1, w2, b2, act="gelu") -> torch.Tensor:
+    B, ci = x.shape[:2]
+    grid = tuple(x.shape[2:])
+    hidden = w1.shape[0]
+    per_sample = b1 is not None and b1.dim() == 2
+    out = torch.empty((B, 1) + grid, dtype=torch.float32, device=x.device)
+    check(_lib.lib().b2no_mlp_head_fwd(_ptr(x), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(out), B, ci, hidden,
+                                       math.prod(grid), 1 if per_sample else 0, ACT[act], _stream()), "mlp_head_fwd")
+    LAUNCHES[0] += 1
+    return out
+
+
+def rno_gate_fwd(z, z2, hh, h):
+    out = torch.empty_like(h)
+    check(_lib.lib().b2no_rno_gate_fwd(_ptr(z), _ptr(z2), _ptr(hh), _ptr(h), _ptr(out), h.numel(), _stream()), "gate")
+    LAUNCHES[0] += 1
+    return out
+
+
+def rno_gate_bwd(g, z, z2, hh, h):
+    outs = [torch.empty_like(h) for _ in range(4)]
+    check(_lib.lib().b2no_rno_gate_bwd(_ptr(g), _ptr(z), _ptr(z2), _ptr(hh), _ptr(h), *[_ptr(o) for o in outs],
+                                       h.numel(), _stream()), "gate_bwd")
+    LAUNCHES[0] += 1
+    return outs
+
+
+def rel_l2_sums(x, y):
+    B = x.shape[0]
+    n = x.numel() // B
+    sums = torch.empty((B, 2), dtype=torch.float32, device=x.device)
+    check(_lib.lib().b2no_rel_l2_sums(_ptr(x), _ptr(y), _ptr(sums), B, n, _stream()), "rel_l2_sums")
+    LAUNCHES[0] += 1
+    return sums
+
+
+def rel_l2_bwd(x, y, coef):
+    B = x.shape[0]
+    dx = torch.empty_like(x)
+    check(_lib.lib().b2no_rel_l2_bwd(_ptr(x), _ptr(y), _ptr(coef), _ptr(dx), B, x.numel() // B, _stream()), "rel_l2_bwd")
+    LAUNCHES[0] += 1
+    return dx

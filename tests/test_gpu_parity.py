@@ -1,0 +1,392 @@
+"""GPU parity: the CUDA path, called through the reference-facing modules (which go through the C ABI in
+libb2no.so), against (1) the committed golden vectors made by the unmodified reference, (2) the float64
+closed-form oracle on seeded inputs, (3) size-independent properties at BASELINE sizes.
+Tolerance: north_star -- relative L2 <= 1e-5 in fp32."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def _dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+def rel(a, b):
+    from oracle.closed_form import rel_l2
+    return rel_l2(a, b)
+
+
+# --------------------------------------------------------------------------------------------
+# raw C-ABI stages vs the closed-form oracle (locates a failure to a kernel)
+# --------------------------------------------------------------------------------------------
+STAGE_CASES = [
+    # nin, half, norm, nfft, nout, Ci, Co, B
+    ((12,), (5,), "forward", None, None, 3, 4, 2),
+    ((16, 12), (4, 3), "forward", None, None, 3, 5, 2),
+    ((128, 128), (6, 6), "forward", None, None, 4, 4, 2),
+    ((64, 64), (8, 8), "backward", None, None, 3, 3, 3),
+    ((32, 32), (12, 12), "ortho", (32, 32), (32, 32), 34, 34, 2),
+    ((9, 11), (3, 3), "ortho", None, None, 2, 3, 2),
+    ((8, 12), (6, 3), "forward", None, None, 2, 2, 2),          # overlap 2h > N
+    ((15, 12), (4, 3), "ortho", (12, 12), (12, 12), 3, 2, 2),   # rno crop
+    ((9, 12), (4, 3), "ortho", (12, 12), (12, 12), 3, 2, 2),    # rno zero-pad
+    ((16, 12), (4, 3), "forward", None, (8, 6), 3, 4, 2),       # output scaling 0.5
+    ((16, 12), (4, 3), "backward", None, (32, 24), 3, 4, 2),    # output scaling 2
+    ((8, 8, 9), (3, 2, 4), "backward", None, None, 3, 4, 2),
+    ((8, 8, 9), (3, 2, 6), "backward", None, None, 3, 4, 2),    # modes3 > Z/2+1
+    ((16, 16, 73), (8, 8, 8), "backward", None, None, 4, 4, 1),
+    ((20, 200), (4, 20), "forward", None, None, 2, 2, 2),       # long rows, many modes (chunked)
+]
+
+
+@pytest.mark.parametrize("case", STAGE_CASES, ids=lambda c: "x".join(map(str, c[0])) + f"-h{'x'.join(map(str, c[1]))}-{c[2]}")
+def test_stages_vs_closed_form(case):
+    from oracle import closed_form as cf
+    from pde_policylearning_b200 import ops
+    nin, half, norm, nfft, nout, ci, co, B = case
+    dev = _dev()
+    torch.manual_seed(7)
+    g64 = cf.SpecGeom(nin=nin, half=half, norm=norm, nfft=nfft, nout=nout)
+    geom = ops.SpecGeom(nin=nin, half=half, norm=norm, nfft=nfft, nout=nout)
+    plan = ops.get_plan(geom, dev)
+    assert plan.kept == g64.kept()
+    sf, si = g64.scales()
+    d = len(nin)
+    x = torch.randn(B, ci, *nin)
+    hshape = tuple(half)
+    corners = [torch.randn(ci, co, *hshape, dtype=torch.cfloat) for _ in range(2 ** (d - 1))]
+    # forward transform
+    xh = ops.dft_forward(plan, 0, x.to(dev).contiguous())
+    xh64 = cf.dft_trunc(g64, x, sf)
+    assert rel(xh, xh64) < TOL, "dft_forward(which=0)"
+    # mixing
+    cd = [c.to(dev) for c in corners]
+    yh = ops.mix(plan, 0, xh, cd, ci, co)
+    W = cf.gather_weight(g64, corners)
+    yh64 = torch.einsum("bi...,io...->bo...", xh64, W)
+    assert rel(yh, yh64) < TOL, "mix(mode=0)"
+    # inverse transform (no epilogue)
+    y = ops.dft_inverse(plan, 0, yh, None)
+    y64 = cf.idft_trunc(g64, yh64, si)
+    assert rel(y, y64) < TOL, "dft_inverse(which=0)"
+    # adjoints
+    gy = torch.randn(B, co, *g64.nout)
+    gyh = ops.dft_forward(plan, 1, gy.to(dev).contiguous())
+    gyh64 = cf.dft_trunc(g64, gy, si, use_inv_conj=True)
+    assert rel(gyh, gyh64) < TOL, "dft_forward(which=1)"
+    gxh = ops.mix(plan, 1, gyh, cd, ci, co)
+    gxh64 = torch.einsum("bo...,io...->bi...", gyh64, W.conj())
+    assert rel(gxh, gxh64) < TOL, "mix(mode=1)"
+    dx = ops.dft_inverse(plan, 1, gxh, None)
+    dx64 = cf.idft_trunc(g64, gxh64, sf, use_fwd_conj=True)
+    assert rel(dx, dx64) < TOL, "dft_inverse(which=1)"
+    overlap = any(2 * half[j] > g64.nfft[j] for j in range(d - 1))
+    dws = ops.mix_dw(plan, xh, gyh, cd, needs_zero=overlap)
+    dW64 = cf.scatter_weight_grad(g64, torch.einsum("bi...,bo...->io...", xh64.conj(), gyh64),
+                                  [tuple(c.shape) for c in corners])
+    for a, b in zip(dws, dW64):
+        if b.abs().max() > 0:
+            assert rel(a, b) < TOL, "mix_dw"
+        else:
+            assert a.abs().max().item() == 0.0
+
+
+def test_epilogue_and_pointwise():
+    """fused epilogue: bias + 1x1 skip + second operand + add + act + mul + preact."""
+    from pde_policylearning_b200 import ops
+    dev = _dev()
+    torch.manual_seed(3)
+    for grid, ci, ci2, co, act in (((16, 12), 5, 3, 7, "gelu"), ((130,), 32, 1, 256, "relu"),
+                                   ((6, 5, 9), 34, 2, 1, "selu"), ((128, 128), 32, 4, 32, "sigmoid"),
+                                   ((64, 64), 3, 2, 32, "tanh")):
+        B = 2
+        x = torch.randn(B, ci, *grid, device=dev)
+        x2 = torch.randn(B, ci2, *grid, device=dev)
+        w = torch.randn(co, ci, device=dev)
+        w2 = torch.randn(co, ci2, device=dev)
+        b = torch.randn(co, device=dev)
+        add = torch.randn(B, co, *grid, device=dev)
+        mul = torch.randn(B, co, *grid, device=dev)
+        z = torch.empty(B, co, *grid, device=dev)
+        y = ops.pointwise(B, co, grid, dev, ops.make_epilogue(bias=b, pw_w=w, pw_x=x, pw2_w=w2, pw2_x=x2, add=add,
+                                                              mul=mul, preact=z, act=act))
+        z64 = (torch.einsum("oi,bi...->bo...", w.double(), x.double()) + torch.einsum("oi,bi...->bo...", w2.double(), x2.double())
+               + b.double().reshape((1, -1) + (1,) * len(grid)) + add.double())
+        f = {"gelu": torch.nn.functional.gelu, "relu": torch.relu, "selu": torch.selu, "sigmoid": torch.sigmoid,
+             "tanh": torch.tanh}[act]
+        assert rel(z, z64) < TOL
+        assert rel(y, f(z64) * mul.double()) < TOL
+        # transposed weight (dx pass)
+        g = torch.randn(B, co, *grid, device=dev)
+        dx = ops.pointwise(B, ci, grid, dev, ops.make_epilogue(pw_w=w, pw_x=g, pw_transposed=True))
+        assert rel(dx, torch.einsum("oi,bo...->bi...", w.double(), g.double())) < TOL
+        # weight gradient
+        dw, db = ops.pw_wgrad(g, x, need_bias=True)
+        assert rel(dw, torch.einsum("bo...,bi...->oi", g.double(), x.double())) < TOL
+        assert rel(db, g.double().sum(dim=[0] + list(range(2, g.dim())))) < TOL
+        # activation backward
+        gz = ops.act_bwd(g, z, act)
+        zz = z.double().requires_grad_(True)
+        (f(zz) * g.double()).sum().backward()
+        assert rel(gz, zz.grad) < TOL
+
+
+def test_mlp_head_rel_l2_gate():
+    from pde_policylearning_b200 import ops
+    import pde_policylearning_b200 as P
+    dev = _dev()
+    torch.manual_seed(4)
+    for ci, hid, grid in ((32, 256, (40, 33)), (64, 128, (5, 6, 7)), (8, 16, (300,))):
+        B = 3
+        x = torch.randn(B, ci, *grid, device=dev)
+        w1, b1 = torch.randn(hid, ci, device=dev) * 0.2, torch.randn(hid, device=dev)
+        w2, b2 = torch.randn(hid, device=dev) * 0.2, torch.randn(1, device=dev)
+        out = ops.mlp_head_fwd(x, w1, b1, w2, b2, "gelu")
+        h = torch.nn.functional.gelu(torch.einsum("ji,bi...->bj...", w1.double(), x.double()) + b1.double().reshape((1, -1) + (1,) * len(grid)))
+        ref = torch.einsum("j,bj...->b...", w2.double(), h).unsqueeze(1) + b2.double()
+        assert rel(out, ref) < TOL
+        b1ps = torch.randn(B, hid, device=dev)
+        out = ops.mlp_head_fwd(x, w1, b1ps, w2, b2, "gelu")
+        h = torch.nn.functional.gelu(torch.einsum("ji,bi...->bj...", w1.double(), x.double()) + b1ps.double().reshape((B, hid) + (1,) * len(grid)))
+        assert rel(out, torch.einsum("j,bj...->b...", w2.double(), h).unsqueeze(1) + b2.double()) < TOL
+    # rel-L2 loss + grad
+    x = torch.randn(5, 1, 37, 41, device=dev, requires_grad=True)
+    y = torch.randn(5, 1, 37, 41, device=dev)
+    for avg in (True, False):
+        loss = P.rel_l2_loss(x, y, avg)
+        xd = x.detach().double().requires_grad_(True)
+        r = torch.norm((xd - y.double()).reshape(5, -1), 2, 1) / torch.norm(y.double().reshape(5, -1), 2, 1)
+        lref = r.mean() if avg else r.sum()
+        assert abs(loss.item() - lref.item()) < 1e-5 * abs(lref.item())
+        (g,) = torch.autograd.grad(loss, x)
+        (gref,) = torch.autograd.grad(lref, xd)
+        assert rel(g, gref) < TOL
+    # gate
+    z, z2, hh, h = (torch.randn(2, 6, 9, 9, device=dev, requires_grad=True) for _ in range(4))
+    out = P.rno_gate(z, z2, hh, h)
+    ref = (1 - z) * h + z2 * hh
+    assert rel(out, ref) < 1e-6
+    go = torch.randn_like(out)
+    for a, b in zip(torch.autograd.grad(out, [z, z2, hh, h], go), torch.autograd.grad(ref, [z, z2, hh, h], go)):
+        assert rel(a, b) < 1e-6
+
+
+# --------------------------------------------------------------------------------------------
+# modules vs golden vectors from the unmodified reference
+# --------------------------------------------------------------------------------------------
+A1 = ["2d_forward", "2d_backward", "2d_ortho", "1d_forward", "3d_forward", "2d_overlap", "2d_oddgrid",
+      "2d_scale_half", "2d_scale_2", "2d_cfg1_small"]
+
+
+def _run_conv(mod, c, dev):
+    mod = mod.to(dev)
+    x = c["x"].to(dev).requires_grad_(True)
+    y = mod(x)
+    names = [n for n, _ in mod.named_parameters()]
+    gs = torch.autograd.grad(y, [x] + [p for _, p in mod.named_parameters()], c["gy"].to(dev))
+    assert rel(y, c["y"]) < TOL, "y"
+    assert rel(gs[0], c["dx"]) < TOL, "dx"
+    for n, g in zip(names, gs[1:]):
+        ref = c["grads"][n]
+        if ref.abs().max() == 0:
+            assert g.abs().max().item() == 0
+        else:
+            assert rel(g, ref) < TOL, n
+
+
+@pytest.mark.parametrize("name", A1)
+def test_golden_neuralop_conv(golden, name):
+    import pde_policylearning_b200 as P
+    c = golden("a1_neuralop_conv")[name]
+    ci, co = c["params"]["weight.0.tensor"].shape[:2]
+    m = P.SpectralConv(ci, co, c["n_modes"], n_layers=1, factorization=None, implementation="factorized",
+                       fft_norm=c["fft_norm"], **c["kw"])
+    m.load_state_dict(c["params"])
+    _run_conv(m, c, _dev())
+
+
+def test_golden_layer_index(golden):
+    import pde_policylearning_b200 as P
+    c = golden("a1_neuralop_conv")["2d_layer_index2"]
+    m = P.SpectralConv(4, 4, (6, 6), n_layers=3, factorization=None, implementation="factorized", fft_norm="forward")
+    m.load_state_dict(c["params"])
+    m = m.to(_dev())
+    assert rel(m(c["x"].to(_dev()), 2), c["y"]) < TOL
+    assert rel(m[2](c["x"].to(_dev())), c["y"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["square", "cfg3_small", "tall", "short"])
+def test_golden_rno_conv(golden, name):
+    import pde_policylearning_b200 as P
+    c = golden("a4_rno_conv")[name]
+    ci, co, m1, m2, _ = c["params"]["fourier_weight.0"].shape
+    m = P.RnoSpectralConv2d(ci, co, m1, m2)
+    m.load_state_dict(c["params"])
+    _run_conv(m, c, _dev())
+
+
+@pytest.mark.parametrize("name", ["basic", "zpad", "cfg4_small"])
+def test_golden_pino_conv(golden, name):
+    import pde_policylearning_b200 as P
+    c = golden("a6_pino_conv")[name]
+    ci, co, m1, m2, m3 = c["params"]["weights1"].shape
+    m = P.PinoSpectralConv3d(ci, co, m1, m2, m3)
+    m.load_state_dict(c["params"])
+    _run_conv(m, c, _dev())
+
+
+def _run_model(mod, c, dev, loss_fn=None, tol=TOL, gtol=5e-5):
+    mod.load_state_dict(c["state_dict"])
+    mod = mod.to(dev)
+    out = mod(*[t.to(dev) for t in c["inputs"]])
+    assert rel(out, c["out"]) < tol, "output"
+    loss = out.square().mean() if loss_fn is None else loss_fn(out)
+    assert abs(loss.item() - c["loss"].item()) <= 2e-5 * abs(c["loss"].item()), "loss"
+    names = [n for n, _ in mod.named_parameters()]
+    gs = torch.autograd.grad(loss, [p for _, p in mod.named_parameters()], allow_unused=True)
+    worst = 0.0
+    for n, g in zip(names, gs):
+        assert g is not None, f"{n} got no gradient"   # test_tfno.py:61-65: every parameter is reached
+        worst = max(worst, rel(g, c["grads"][n]))
+        assert rel(g, c["grads"][n]) < gtol, n
+    return worst
+
+
+def test_golden_fno2d(golden):
+    import pde_policylearning_b200 as P
+    c = golden("a3_fno2d")
+    dev = _dev()
+    m = P.FNO2d(8, 8, 16, in_channels=3, out_channels=1)
+    tgt = c["target"].to(dev)
+    _run_model(m, c, dev, lambda o: P.rel_l2_loss(o, tgt, size_average=False))
+
+
+def test_golden_fno3d_and_observer(golden):
+    import pde_policylearning_b200 as P
+    dev = _dev()
+    c = golden("a3_fno3d")
+    _run_model(P.FNO3d(4, 4, 4, 6, in_channels=2, out_channels=1), c, dev)
+    c = golden("a9_fno2d_observer")
+    _run_model(P.FNO2dObserver(6, 6, 8), c, dev)
+
+
+def test_golden_rno(golden):
+    import pde_policylearning_b200 as P
+    dev = _dev()
+    c = golden("a5_rno_cell")
+    _run_model(P.RNO_cell(6, 6, 4, 4, 6), c, dev)
+    c = golden("a5_rno2d_L1")
+    _run_model(P.RNO2d(4, 4, 6, 0, layer_num=1).eval(), c, dev, gtol=2e-4)
+    c = golden("a5_rno2d_L2")
+    _run_model(P.RNO2d(4, 4, 6, 1, layer_num=2).eval(), c, dev, gtol=2e-4)
+
+
+def test_golden_pinobserver(golden):
+    import pde_policylearning_b200 as P
+    from oracle import restated as rs
+    dev = _dev()
+    c = golden("a7_pinobserver2d")
+    m = P.PINObserver2d(modes1=[3] * 3, modes2=[3] * 3, modes3=[3] * 3, fc_dim=16, layers=[8] * 4, act="gelu",
+                        pad_ratio=0.0625)
+    u, re = c["u"].to(dev), c["inputs"][1].to(dev)
+    forcing = rs.get_forcing(8).to(dev)
+
+    def loss_fn(o):
+        data = P.rel_l2_loss(o.reshape(2, 8, 8, 17), u, True)
+        lic, lf = rs.channelflow_pino_loss(o, u[..., 0], forcing, 1 / re, c["t_interval"])
+        return 5.0 * data + lf + lic
+
+    _run_model(m, c, dev, loss_fn, gtol=2e-4)
+    # inference path (fused head) gives the same output
+    with torch.no_grad():
+        out = m(*[t.to(dev) for t in c["inputs"]])
+    assert rel(out, c["out"]) < TOL
+
+
+# --------------------------------------------------------------------------------------------
+# BASELINE-size checks: restated torch.fft oracle on the same device + size-independent properties
+# --------------------------------------------------------------------------------------------
+def test_cfg1_full_size_vs_closed_form():
+    """BASELINE config 1: FactorizedSpectralConv(32,32,(16,16)) on (8,32,64,64), fwd+bwd."""
+    import pde_policylearning_b200 as P
+    from oracle import closed_form as cf
+    dev = _dev()
+    torch.manual_seed(11)
+    m = P.SpectralConv(32, 32, (16, 16), n_layers=1, factorization=None, implementation="factorized", fft_norm="forward")
+    x = torch.randn(8, 32, 64, 64)
+    gy = torch.randn(8, 32, 64, 64)
+    geom = cf.geom_neuralop((64, 64), (16, 16), "forward")
+    corners = [w.tensor.detach() for w in m.weight]
+    y64, _, _ = cf.spectral_conv_forward(geom, x, corners, m.bias.detach()[0].flatten())
+    dx64, dW64, db64 = cf.spectral_conv_backward(geom, x, corners, gy, has_bias=True)
+    m = m.to(dev)
+    xd = x.to(dev).requires_grad_(True)
+    y = m(xd)
+    gs = torch.autograd.grad(y, [xd, m.weight[0].tensor, m.weight[1].tensor, m.bias], gy.to(dev))
+    assert rel(y, y64) < TOL
+    assert rel(gs[0], dx64) < TOL
+    assert rel(gs[1], dW64[0]) < TOL and rel(gs[2], dW64[1]) < TOL
+    assert rel(gs[3].flatten(), db64) < TOL
+
+
+def test_cfg2_fno2d_full_size_vs_restated():
+    """BASELINE config 2 (batch 8 of the 64): FNO2d(12,12,32) 128x128 fwd+bwd against the restated
+    reference algorithm (torch.fft + einsum, float64) on the same inputs."""
+    import pde_policylearning_b200 as P
+    from oracle import restated as rs
+    dev = _dev()
+    torch.manual_seed(12)
+    m = P.FNO2d(12, 12, 32, in_channels=3, out_channels=1).to(dev)
+    x = torch.randn(8, 3, 128, 128, device=dev)
+    tgt = torch.randn(8, 1, 128, 128, device=dev)
+    out = m(x)
+    loss = P.rel_l2_loss(out, tgt, size_average=False)
+    names = [n for n, _ in m.named_parameters()]
+    gs = torch.autograd.grad(loss, [p for _, p in m.named_parameters()])
+    sd = {}
+    for k, v in m.state_dict().items():
+        v = v.detach()
+        sd[k] = (v.to(torch.complex128) if v.is_complex() else v.double()).requires_grad_(True)
+    out64 = rs.fno_forward(sd, x.double(), (12, 12))
+    loss64 = rs.lp_rel(out64, tgt.double(), size_average=False)
+    gs64 = torch.autograd.grad(loss64, [sd[n] for n in names])
+    assert rel(out, out64) < TOL
+    assert abs(loss.item() - loss64.item()) < 1e-5 * abs(loss64.item())
+    for n, a, b in zip(names, gs, gs64):
+        assert rel(a, b) < 5e-5, n
+
+
+def test_properties_full_size():
+    """Size-independent properties at BASELINE config 2/3/4 shapes: linearity, the adjoint identity
+    <conv(x), g> == <x, conv^T(g)>, translation equivariance and the DC-mode bias gradient."""
+    import pde_policylearning_b200 as P
+    dev = _dev()
+    torch.manual_seed(13)
+    cases = [
+        (P.SpectralConv(32, 32, (12, 12), bias=False, factorization=None, implementation="factorized",
+                        fft_norm="forward"), (16, 32, 128, 128)),
+        (P.RnoSpectralConv2d(34, 34, 12, 12), (32, 34, 32, 32)),
+        (P.PinoSpectralConv3d(16, 16, 8, 8, 8), (1, 16, 32, 32, 73)),
+    ]
+    for m, shape in cases:
+        m = m.to(dev)
+        x1 = torch.randn(*shape, device=dev, requires_grad=True)
+        x2 = torch.randn(*shape, device=dev)
+        y1 = m(x1)
+        y2 = m(x2)
+        y12 = m(2.0 * x1.detach() - 3.0 * x2)
+        assert rel(y12, 2.0 * y1.detach() - 3.0 * y2) < TOL, "linearity"
+        g = torch.randn_like(y1)
+        (dx,) = torch.autograd.grad(y1, x1, g)
+        lhs = (y1.detach().double() * g.double()).sum().item()
+        rhs = (x1.detach().double() * dx.double()).sum().item()
+        assert abs(lhs - rhs) < 1e-5 * max(abs(lhs), abs(rhs), 1e-3 * y1.detach().double().norm().item() * g.double().norm().item()), "adjoint"
+        # circular shift along the last axis commutes with the convolution
+        ys = m(torch.roll(x2, shifts=5, dims=-1))
+        assert rel(ys, torch.roll(y2, shifts=5, dims=-1)) < TOL, "translation equivariance"

@@ -1,0 +1,127 @@
+"""CPU: host-side logic, the C ABI surface, state_dict / drop-in contracts.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pde_policylearning_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    hdr = open(os.path.join(ROOT, "include", "b2no.h")).read()
+    declared = set(re.findall(r"\b(b2no_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 19
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/b2no.h but not exported"
+    assert set(_lib.EXPORTS) == declared
+    assert _lib.lib().b2no_version() == 1
+    assert b"bad argument" in _lib.lib().b2no_error_string(-1)
+
+
+def test_no_cpu_fallback():
+    import pde_policylearning_b200 as P
+    m = P.SpectralConv(3, 3, (4, 4), factorization=None, implementation="factorized")
+    with pytest.raises(RuntimeError, match="no CPU fallback|only on CUDA"):
+        m(torch.randn(1, 3, 8, 8))
+    with pytest.raises(RuntimeError):
+        P.pointwise_conv(torch.randn(1, 3, 8, 8), torch.randn(4, 3), None, None)
+    with pytest.raises(RuntimeError):
+        P.rel_l2_loss(torch.randn(2, 5), torch.randn(2, 5))
+
+
+def test_unsupported_options_raise():
+    import pde_policylearning_b200 as P
+    with pytest.raises(NotImplementedError):
+        P.SpectralConv(3, 3, (4, 4), factorization="cp")
+    with pytest.raises(NotImplementedError):
+        P.SpectralConv(3, 3, (4, 4), factorization=None, separable=True)
+    with pytest.raises(ValueError):
+        P.SpectralConv(3, 3, (4, 4), factorization=None, implementation="bogus")
+    with pytest.raises(NotImplementedError):
+        P.FNO((4, 4), 8, use_mlp=True)
+    with pytest.raises(ValueError):
+        P.SpectralConv(3, 3, (4, 4), factorization=None, incremental_n_modes=(2, 2, 2))
+
+
+def test_state_dict_layout_matches_golden(golden):
+    """Parameter names / shapes / dtypes are the reference's."""
+    import pde_policylearning_b200 as P
+    pairs = [
+        (P.FNO2d(8, 8, 16, in_channels=3, out_channels=1), golden("a3_fno2d")["state_dict"]),
+        (P.FNO3d(4, 4, 4, 6, in_channels=2, out_channels=1), golden("a3_fno3d")["state_dict"]),
+        (P.FNO2dObserver(6, 6, 8), golden("a9_fno2d_observer")["state_dict"]),
+        (P.RNO2d(4, 4, 6, 0, layer_num=1), golden("a5_rno2d_L1")["state_dict"]),
+        (P.RNO2d(4, 4, 6, 1, layer_num=2), golden("a5_rno2d_L2")["state_dict"]),
+        (P.RNO_cell(6, 6, 4, 4, 6), golden("a5_rno_cell")["state_dict"]),
+        (P.PINObserver2d(modes1=[3] * 3, modes2=[3] * 3, modes3=[3] * 3, fc_dim=16, layers=[8] * 4, act="gelu",
+                         pad_ratio=0.0625), golden("a7_pinobserver2d")["state_dict"]),
+    ]
+    for mod, sd in pairs:
+        mine = {k: (tuple(v.shape), v.dtype) for k, v in mod.state_dict().items()}
+        ref = {k: (tuple(v.shape), v.dtype) for k, v in sd.items()}
+        assert mine == ref
+        mod.load_state_dict(sd)
+
+
+def test_real_view_checkpoint_loads():
+    """tltorch >= 0.4 stores ComplexDense weights as a real view (..., 2): accept both."""
+    import pde_policylearning_b200 as P
+    m = P.SpectralConv(3, 4, (4, 4), factorization=None, implementation="factorized")
+    sd = {k: (torch.view_as_real(v).clone() if v.is_complex() else v.clone()) for k, v in m.state_dict().items()}
+    m2 = P.SpectralConv(3, 4, (4, 4), factorization=None, implementation="factorized")
+    m2.load_state_dict(sd)
+    assert torch.equal(m2.weight[0].tensor, m.weight[0].tensor)
+
+
+def test_incremental_modes_and_quirks():
+    import pde_policylearning_b200 as P
+    m = P.SpectralConv(3, 4, (8, 6), factorization=None, implementation="factorized", n_layers=2)
+    assert m.half_n_modes == [4, 3] and m.n_weights_per_layer == 2 and len(m.weight) == 4
+    m.incremental_n_modes = (4, 4)
+    assert m.half_n_modes == [2, 2]
+    assert tuple(m._get_weight(1).shape) == (3, 4, 2, 2)
+    blocks = P.FNOBlocks(8, 8, (4, 4), n_layers=4)
+    # quirk Q1: activation iff index < n_layers - index  -> layers 0, 1 only
+    assert [i < (blocks.n_layers - i) for i in range(4)] == [True, True, False, False]
+    f = P.FNO2d(4, 4, 8, skip="soft-gating")    # quirk Q2: `skip=` is swallowed, skips stay linear
+    assert isinstance(f.fno_blocks.fno_skips[0], torch.nn.Conv2d) and f.fno_blocks.fno_skips[0].bias is None
+    r = P.RNO2d(3, 5, 6, 0, layer_num=1)
+    assert r.modes1 == 5                         # quirk Q4
+    assert r.regressor.spectral_conv[0].dropout.p == 0.3
+
+
+def test_geometry_matches_oracle():
+    from oracle import closed_form as cf
+    from pde_policylearning_b200.ops import SpecGeom
+    for nin, half, norm, nfft, nout in (((16, 12), (4, 3), "forward", None, None),
+                                        ((15, 12), (4, 3), "ortho", (12, 12), (12, 12)),
+                                        ((16, 12), (4, 3), "backward", None, (32, 24))):
+        a = SpecGeom(nin, half, norm, nfft, nout).resolved()
+        b = cf.SpecGeom(nin=nin, half=half, norm=norm, nfft=nfft, nout=nout)
+        assert a.nfft == b.nfft and a.nout == b.nout
+        assert a.scales() == pytest.approx(b.scales())
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/neuralop"), reason="reference tree only exists in the build container")
+def test_convert_shares_parameters_with_reference_modules():
+    import pde_policylearning_b200 as P
+    from oracle import ref_loader
+    ref = ref_loader.load()
+    for build in (lambda: ref.FNO2d(12, 12, 32, in_channels=3, out_channels=1),
+                  lambda: ref.RNO2d(12, 12, 34, 0, layer_num=1),
+                  lambda: ref.PINObserver2d(modes1=[3] * 3, modes2=[3] * 3, modes3=[3] * 3, fc_dim=16, layers=[8] * 4,
+                                            act="gelu", pad_ratio=0.0625)):
+        r = build()
+        before = {k: v.data_ptr() for k, v in r.named_parameters()}
+        keys = list(r.state_dict().keys())
+        c = P.convert_(r)
+        assert {k: v.data_ptr() for k, v in c.named_parameters()} == before
+        assert list(c.state_dict().keys()) == keys
+        native = [m for m in c.modules() if type(m).__module__.startswith("pde_policylearning_b200")]
+        assert native, "nothing was converted"
