@@ -266,7 +266,7 @@ def fdm_ns_vorticity(w, v, t_interval=1.0):
     wh = torch.fft.fft2(w, dim=[1, 2])
     kmax = nx // 2
     N = nx
-    k1 = torch.cat((torch.arange(0, kmax), torch.arange(-kmax, 0)), 0).to(dt_)
+    k1 = torch.cat((torch.arange(0, kmax), torch.arange(-kmax, 0)), 0).to(dt_).to(w.device)
     kx = k1.reshape(N, 1).repeat(1, N).reshape(1, N, N, 1)
     ky = k1.reshape(1, N).repeat(N, 1).reshape(1, N, N, 1)
     lap = kx ** 2 + ky ** 2
