@@ -187,7 +187,7 @@ def kernel_probes(dev, hbm_peak_gbs):
     state = {"i": 0}
     L = ops._lib.lib()
     import ctypes as Cc
-    work = plan.workspace(B * C)
+    work = plan.workspace(B, C)
     outs = [torch.empty(B, C, N, N, device=dev) for _ in range(nbuf)]
     A = torch.empty(B * C * N, plan.kept[1], dtype=torch.complex64, device=dev)
     st = Cc.c_void_p(torch.cuda.current_stream().cuda_stream)

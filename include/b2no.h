@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define B2NO_MAX_DIM 3
-#define B2NO_ABI_VERSION 1
+#define B2NO_ABI_VERSION 2
 
 enum { B2NO_NORM_BACKWARD = 0, B2NO_NORM_FORWARD = 1, B2NO_NORM_ORTHO = 2 };
 enum { B2NO_ACT_NONE = 0, B2NO_ACT_GELU = 1, B2NO_ACT_RELU = 2, B2NO_ACT_SIGMOID = 3, B2NO_ACT_SELU = 4,
@@ -72,7 +72,7 @@ typedef struct {
 
 /* Fused epilogue of the inverse transform:
  *   z = irfft(Yh) + bias[o] + sum_i pw_w[o,i] * pw_x[b,i,.] + sum_i pw2_w[o,i] * pw2_x[b,i,.] + add[b,o,.]
- *   y = act(z) * (mul ? mul[b,o,.] : 1)
+ *   y = act(z) * (mul ? mul[b,o,.] : 1) * (dact_z ? dact'(dact_z[b,o,.]) : 1)
  * (fno_block.py:131,142-150; rno.py:224-228,254-258; pinobserver.py:222-226).  pw_w is (Co, Ci) row-major,
  * or (Ci, Co) when pw_transposed (the dx pass of the 1x1 conv).  preact, when non-NULL, receives z. */
 typedef struct {
@@ -83,6 +83,10 @@ typedef struct {
   const float* mul;
   float* preact;
   int32_t act;
+  /* backward chaining: multiply by the derivative of activation `dact` evaluated at the saved
+   * pre-activation dact_z of the PREVIOUS layer, so a layer's dx pass emits gz of the layer below directly */
+  const float* dact_z;
+  int32_t dact;
 } b2no_epilogue;
 
 int b2no_version(void);
@@ -94,8 +98,13 @@ int b2no_plan_create(const b2no_geom* geom, b2no_plan** out);
 int b2no_plan_destroy(b2no_plan* plan);
 /* kept modes per dim (K_j) */
 int b2no_plan_kept(const b2no_plan* plan, int32_t kept[B2NO_MAX_DIM]);
-/* floats of scratch needed by dft_forward / dft_inverse for `bc` (batch*channel) images */
-int64_t b2no_plan_workspace_floats(const b2no_plan* plan, int64_t bc);
+/* floats of scratch needed by dft_forward / dft_inverse for a (batch, channels) tensor */
+int64_t b2no_plan_workspace_floats(const b2no_plan* plan, int64_t batch, int64_t channels);
+/* 1 = use the tcgen05 tensor-core kernels where the shape is eligible (default on sm_100), 0 = CUDA-core kernels
+ * only.  Returns the mode now in force.  Both paths are CUDA; neither is a CPU fallback. */
+int b2no_set_tensor_core_mode(int on);
+/* number of tcgen05 kernel launches issued so far by this process (evidence for tests / bench) */
+int64_t b2no_tensor_core_launches(void);
 
 /* ---- truncated transforms ---------------------------------------------------------------------- */
 /* which = 0: Xh = s_f * DFT_trunc(x)            x on the nin grid    (rfftn + slicing)

@@ -11,7 +11,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2no.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["plan.cu", "spectral.cu", "pointwise.cu"]
+SOURCES = ["plan.cu", "spectral.cu", "pointwise.cu", "tc_pointwise.cu"]
 
 MAX_DIM = 3
 NORM = {"backward": 0, "forward": 1, "ortho": 2}
@@ -32,7 +32,8 @@ class Epilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p),
                 ("pw_w", C.c_void_p), ("pw_x", C.c_void_p), ("pw_ci", C.c_int32), ("pw_transposed", C.c_int32),
                 ("pw2_w", C.c_void_p), ("pw2_x", C.c_void_p), ("pw2_ci", C.c_int32), ("pw2_transposed", C.c_int32),
-                ("add", C.c_void_p), ("mul", C.c_void_p), ("preact", C.c_void_p), ("act", C.c_int32)]
+                ("add", C.c_void_p), ("mul", C.c_void_p), ("preact", C.c_void_p), ("act", C.c_int32),
+                ("dact_z", C.c_void_p), ("dact", C.c_int32)]
 
 
 def nvcc_command(out_path: str = LIB_PATH):
@@ -43,7 +44,7 @@ def nvcc_command(out_path: str = LIB_PATH):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu for sm_100a into libb2no.so (in-tree, so it travels with the repo snapshot)."""
-    srcs = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"),
+    srcs = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc.cuh"),
                                                        os.path.join(_HERE, "..", "include", "b2no.h")]
     if not force and os.path.exists(LIB_PATH):
         newest = max(os.path.getmtime(s) for s in srcs)
@@ -77,7 +78,9 @@ def lib():
     L.b2no_plan_destroy.argtypes = [vp]
     L.b2no_plan_kept.argtypes = [vp, C.POINTER(C.c_int32 * MAX_DIM)]
     L.b2no_plan_workspace_floats.restype = i64
-    L.b2no_plan_workspace_floats.argtypes = [vp, i64]
+    L.b2no_plan_workspace_floats.argtypes = [vp, i64, i64]
+    L.b2no_set_tensor_core_mode.argtypes = [i32]
+    L.b2no_tensor_core_launches.restype = i64
     L.b2no_dft_forward.argtypes = [vp, i32, vp, vp, vp, i64, vp]
     L.b2no_dft_inverse.argtypes = [vp, i32, vp, vp, vp, i32, i32, i64, C.POINTER(Epilogue), vp]
     L.b2no_mix.argtypes = [vp, i32, vp, C.POINTER(Weights), vp, i32, i32, i32, i32, vp]
@@ -102,6 +105,7 @@ def lib():
 EXPORTS = [
     "b2no_version", "b2no_error_string", "b2no_device_info",
     "b2no_plan_create", "b2no_plan_destroy", "b2no_plan_kept", "b2no_plan_workspace_floats",
+    "b2no_set_tensor_core_mode", "b2no_tensor_core_launches",
     "b2no_dft_forward", "b2no_dft_inverse", "b2no_mix", "b2no_mix_dw",
     "b2no_act_bwd", "b2no_pw_wgrad_scratch_floats", "b2no_pw_wgrad", "b2no_mlp_head_fwd",
     "b2no_rno_gate_fwd", "b2no_rno_gate_bwd", "b2no_rel_l2_sums", "b2no_rel_l2_bwd",

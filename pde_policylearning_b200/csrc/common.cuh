@@ -20,9 +20,20 @@ static inline int b2no_ceil_div(long a, long b) { return (int)((a + b - 1) / b);
 static inline int b2no_round_up(int a, int b) { return ((a + b - 1) / b) * b; }
 
 int b2no_sm_count();   // cached, current device
+bool b2no_tc_available();
+int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float* y, float* work, int batch, int channels,
+                      long pixels, const b2no_epilogue* e, cudaStream_t st);
+
+// operand images for the tensor-core tile kernel (tc_pointwise.cu): the last-dim inverse table as a
+// block-diagonal [128 x Ks] K-major matrix, hi then lo (3xTF32), ready to be copied into shared memory
+struct b2no_tc_tables {
+  float* timg;     // 2 * 128 * Ks floats, or nullptr when the geometry is not eligible
+  int Ks, Qp, R;   // Ks = R * Qp, R = rows per 128-pixel tile, Qp = 2*K_last rounded up to 8
+};
 
 struct b2no_plan {
   b2no_geom g;
+  b2no_tc_tables tc[2];  // [0]: inverse on the nout grid, [1]: adjoint of the forward on the nin grid
   int K[B2NO_MAX_DIM];   // kept modes per dim
   int device;
   // last-dim real tables, layout [qpad][npad] (q = 2k -> re, 2k+1 -> im), zero padded

@@ -79,6 +79,17 @@ int upload(T** dst, const std::vector<T>& v) {
   return 0;
 }
 
+// round-to-nearest (ties away) fp32 -> tf32, like cvt.rna.tf32.f32
+float tf32_round_host(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return x;
+  u += 0x1000u;
+  u &= 0xFFFFE000u;
+  memcpy(&x, &u, 4);
+  return x;
+}
+
 void choose_chunks(int q2, int* qc, int* nchunk) {
   if (q2 <= 4) { *qc = 4; *nchunk = 1; return; }
   if (q2 <= 8) { *qc = 8; *nchunk = 1; return; }
@@ -155,6 +166,31 @@ extern "C" int b2no_plan_create(const b2no_geom* g, b2no_plan** out) {
     int rc;
     if ((rc = upload(&p->t_in, tin))) return rc;
     if ((rc = upload(&p->t_out, tout))) return rc;
+    // tensor-core operand images (2-D and up, last dim dividing the 128-pixel tile)
+    for (int which = 0; which < 2; which++) {
+      const int Wd = which == 0 ? Np : nin;
+      const std::vector<float>& tab = which == 0 ? tout : tin;
+      const int npad = which == 0 ? p->npad_out : p->npad_in;
+      b2no_tc_tables& tt = p->tc[which];
+      tt.timg = nullptr;
+      if (d < 2 || Wd > 128 || 128 % Wd != 0) continue;
+      tt.R = 128 / Wd;
+      tt.Qp = b2no_round_up(2 * K, 8);
+      tt.Ks = tt.R * tt.Qp;
+      if (tt.Ks > 128) continue;
+      std::vector<float> img((size_t)2 * 128 * tt.Ks, 0.f);
+      for (int m = 0; m < 128; m++)
+        for (int k = 0; k < tt.Ks; k++) {
+          const int r = k / tt.Qp, q = k % tt.Qp;
+          float v = 0.f;
+          if (r == m / Wd && q < 2 * K) v = tab[(size_t)q * npad + (m % Wd)];
+          const float hi = tf32_round_host(v);
+          const size_t off = ((size_t)(m >> 3) * (tt.Ks >> 2) * 128 + (size_t)(k >> 2) * 128 + (m & 7) * 16 + (k & 3) * 4) / 4;
+          img[off] = hi;
+          img[(size_t)128 * tt.Ks + off] = tf32_round_host(v - hi);
+        }
+      if ((rc = upload(&tt.timg, img))) return rc;
+    }
   }
 
   // ---- middle dims (complex matrices) -------------------------------------------------------
@@ -200,6 +236,8 @@ extern "C" int b2no_plan_destroy(b2no_plan* p) {
   if (!p) return 0;
   cudaFree(p->t_in);
   cudaFree(p->t_out);
+  cudaFree(p->tc[0].timg);
+  cudaFree(p->tc[1].timg);
   for (int j = 0; j < 2; j++) {
     cudaFree(p->m_fwd[j]); cudaFree(p->m_inv[j]); cudaFree(p->m_adjinv[j]); cudaFree(p->m_adjfwd[j]);
     cudaFree(p->row_corner[j]); cudaFree(p->row_local[j]);
@@ -214,8 +252,9 @@ extern "C" int b2no_plan_kept(const b2no_plan* p, int32_t kept[B2NO_MAX_DIM]) {
   return 0;
 }
 
-extern "C" int64_t b2no_plan_workspace_floats(const b2no_plan* p, int64_t bc) {
-  if (!p || bc < 0) return B2NO_E_ARG;
+extern "C" int64_t b2no_plan_workspace_floats(const b2no_plan* p, int64_t batch, int64_t channels) {
+  if (!p || batch < 0 || channels < 0) return B2NO_E_ARG;
+  const int64_t bc = batch * channels;
   const int d = p->g.ndim;
   if (d == 1) return 0;
   // stage buffers (complex): A = [bc * n_0..n_{d-2}][K_last];  B (3-D only) = [bc * n_0][K_1][K_2]
@@ -228,6 +267,12 @@ extern "C" int64_t b2no_plan_workspace_floats(const b2no_plan* p, int64_t bc) {
     if (d == 3) b = bc * n[0] * p->K[1] * p->K[2];
     int64_t tot = 2 * (a + b);
     if (tot > best) best = tot;
+    // tensor-core path: A' rows (hi + lo), [batch][rows][Qp][channels rounded up to 16]
+    if (d == 2 && p->tc[which].timg) {
+      const int64_t np = (channels + 15) / 16 * 16;
+      const int64_t t = 2 * batch * n[0] * p->tc[which].Qp * np;
+      if (t > best) best = t;
+    }
   }
   return best;
 }

@@ -389,6 +389,8 @@ struct EpiDev {
   const float* mul;
   float* preact;
   int act;
+  const float* dz;
+  int dact;
 };
 
 template <int NPT, int OT>
@@ -509,6 +511,7 @@ k_c2r_fused(const float2* __restrict__ spec, float* __restrict__ y, const float*
             if (e.preact) e.preact[idx] = z;
             float v = b2no_act(z, e.act);
             if (e.mul) v *= __ldg(e.mul + idx);
+            if (e.dz) v *= b2no_act_grad(__ldg(e.dz + idx), e.dact);
             y[idx] = v;
           }
         }
@@ -557,7 +560,19 @@ extern "C" int b2no_dft_inverse(const b2no_plan* p, int which, const float* spec
     e.pw_w = epi->pw_w; e.pw_x = epi->pw_x; e.pw_ci = (epi->pw_w && epi->pw_x) ? epi->pw_ci : 0; e.pw_t = epi->pw_transposed;
     e.pw2_w = epi->pw2_w; e.pw2_x = epi->pw2_x; e.pw2_ci = (epi->pw2_w && epi->pw2_x) ? epi->pw2_ci : 0; e.pw2_t = epi->pw2_transposed;
     e.add = epi->add; e.mul = epi->mul; e.preact = epi->preact; e.act = epi->act;
+    e.dz = epi->dact_z; e.dact = epi->dact_z ? epi->dact : 0;
     if (e.pw_ci < 0 || e.pw2_ci < 0) return B2NO_E_ARG;
+  }
+  // tensor-core tile kernel when the shape is eligible (tc_pointwise.cu); otherwise the CUDA-core kernels below
+  if (epi && (spec == nullptr || (p && p->g.ndim == 2))) {
+    long px = pixels;
+    if (spec && p) {
+      const int32_t* nn = which == 0 ? p->g.nout : p->g.nin;
+      px = (long)nn[0] * nn[1];
+      if (pixels > 0 && pixels != px) return B2NO_E_ARG;
+    }
+    const int rc = b2no_tc_pointwise(p, which, spec, y, work, batch, channels, px, epi, st);
+    if (rc != 1) return rc;
   }
   if (!spec) {
     // pure pointwise op on a flattened grid

@@ -17,6 +17,15 @@ from ._lib import ACT, NORM, Epilogue, Geom, Weights, check
 LAUNCHES = [0]
 
 
+def set_tensor_core_mode(on: bool) -> bool:
+    """Toggle the tcgen05 kernels (both settings are CUDA paths; used by tests and A/B measurements)."""
+    return bool(_lib.lib().b2no_set_tensor_core_mode(1 if on else 0))
+
+
+def tensor_core_launches() -> int:
+    return int(_lib.lib().b2no_tensor_core_launches())
+
+
 def _require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
@@ -93,8 +102,8 @@ class Plan:
         self.modes = math.prod(self.kept)
         self.s_f, self.s_i = g.scales()
 
-    def workspace(self, bc: int) -> Optional[torch.Tensor]:
-        n = int(_lib.lib().b2no_plan_workspace_floats(self.handle, bc))
+    def workspace(self, batch: int, channels: int) -> Optional[torch.Tensor]:
+        n = int(_lib.lib().b2no_plan_workspace_floats(self.handle, batch, channels))
         if n < 0:
             check(n, "workspace")
         if n == 0:
@@ -163,7 +172,7 @@ def dft_forward(plan: Plan, which: int, x: torch.Tensor) -> torch.Tensor:
     if tuple(x.shape[2:]) != tuple(grid):
         raise ValueError(f"expected grid {tuple(grid)}, got {tuple(x.shape[2:])}")
     spec = torch.empty((B, Cc) + plan.kept, dtype=torch.complex64, device=x.device)
-    work = plan.workspace(B * Cc)
+    work = plan.workspace(B, Cc)
     check(_lib.lib().b2no_dft_forward(plan.handle, which, _ptr(x), _ptr(spec), _ptr(work), B * Cc, _stream()),
           "dft_forward")
     LAUNCHES[0] += plan.geom.ndim
@@ -171,11 +180,11 @@ def dft_forward(plan: Plan, which: int, x: torch.Tensor) -> torch.Tensor:
 
 
 def make_epilogue(bias=None, pw_w=None, pw_x=None, pw_transposed=False, pw2_w=None, pw2_x=None,
-                  pw2_transposed=False, add=None, mul=None, preact=None, act=None) -> Epilogue:
+                  pw2_transposed=False, add=None, mul=None, preact=None, act=None, dact_z=None, dact=None) -> Epilogue:
     e = Epilogue()
     keep = []
     for name, t in (("bias", bias), ("pw_w", pw_w), ("pw_x", pw_x), ("pw2_w", pw2_w), ("pw2_x", pw2_x),
-                    ("add", add), ("mul", mul), ("preact", preact)):
+                    ("add", add), ("mul", mul), ("preact", preact), ("dact_z", dact_z)):
         if t is not None:
             _require_cuda(t)
             assert t.dtype == torch.float32 and t.is_contiguous(), name
@@ -188,6 +197,7 @@ def make_epilogue(bias=None, pw_w=None, pw_x=None, pw_transposed=False, pw2_w=No
         e.pw2_ci = pw2_x.shape[1]
         e.pw2_transposed = 1 if pw2_transposed else 0
     e.act = ACT[act]
+    e.dact = ACT[dact] if dact_z is not None else 0
     e._keep = keep
     return e
 
@@ -201,7 +211,7 @@ def dft_inverse(plan: Plan, which: int, spec: torch.Tensor, epi: Optional[Epilog
         raise ValueError(f"expected kept modes {plan.kept}, got {tuple(spec.shape[2:])}")
     grid = plan.geom.nout if which == 0 else plan.geom.nin
     y = torch.empty((B, Cc) + tuple(grid), dtype=torch.float32, device=spec.device)
-    work = plan.workspace(B * Cc)
+    work = plan.workspace(B, Cc)
     check(_lib.lib().b2no_dft_inverse(plan.handle, which, _ptr(spec), _ptr(y), _ptr(work), B, Cc,
                                       math.prod(grid), C.byref(epi) if epi is not None else None, _stream()),
           "dft_inverse")

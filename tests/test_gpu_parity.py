@@ -390,3 +390,55 @@ def test_properties_full_size():
         # circular shift along the last axis commutes with the convolution
         ys = m(torch.roll(x2, shifts=5, dims=-1))
         assert rel(ys, torch.roll(y2, shifts=5, dims=-1)) < TOL, "translation equivariance"
+
+
+# --------------------------------------------------------------------------------------------
+# tcgen05 tile kernel (tc_pointwise.cu): same C-ABI call, tensor-core path vs CUDA-core path vs float64
+# --------------------------------------------------------------------------------------------
+TC_CASES = [
+    # grid, half, norm, ci, co, B, act
+    ((128, 128), (6, 6), "forward", 32, 32, 3, "gelu"),
+    ((64, 64), (8, 8), "forward", 32, 32, 2, None),
+    ((16, 16), (4, 4), "forward", 16, 16, 2, "gelu"),
+    ((32, 64), (5, 7), "backward", 3, 20, 2, "relu"),
+    ((128, 128), (6, 6), "ortho", 8, 40, 1, "tanh"),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "x".join(map(str, c[0])) + f"-c{c[3]}-{c[4]}")
+def test_tensor_core_tile_kernel(case):
+    from oracle import closed_form as cf
+    from pde_policylearning_b200 import ops
+    grid, half, norm, ci, co, B, act = case
+    dev = _dev()
+    torch.manual_seed(11)
+    g64 = cf.SpecGeom(nin=grid, half=half, norm=norm)
+    plan = ops.get_plan(ops.SpecGeom(nin=grid, half=half, norm=norm), dev)
+    sf, si = g64.scales()
+    x = torch.randn(B, ci, *grid)
+    yh = torch.randn(B, co, *plan.kept, dtype=torch.cfloat)
+    w = torch.randn(co, ci)
+    bias = torch.randn(co)
+    dzt = torch.randn(B, co, *grid)
+    f = {"gelu": torch.nn.functional.gelu, "relu": torch.relu, "tanh": torch.tanh, None: lambda t: t}[act]
+    z64 = cf.idft_trunc(g64, yh.to(torch.complex128), si) + torch.einsum("oi,bi...->bo...", w.double(), x.double()) \
+        + bias.double().reshape(1, -1, 1, 1)
+    y64 = f(z64)
+    zz = dzt.double().requires_grad_(True)
+    torch.nn.functional.gelu(zz).sum().backward()
+    y64_d = z64 * zz.grad
+    xd, yhd, wd, bd, dzd = x.to(dev), yh.to(dev), w.to(dev), bias.to(dev), dzt.to(dev)
+    outs = {}
+    try:
+        for mode in (True, False):
+            assert ops.set_tensor_core_mode(mode) == mode
+            n0 = ops.tensor_core_launches()
+            z = torch.empty(B, co, *grid, device=dev)
+            y = ops.dft_inverse(plan, 0, yhd, ops.make_epilogue(bias=bd, pw_w=wd, pw_x=xd, preact=z, act=act))
+            yd = ops.dft_inverse(plan, 0, yhd, ops.make_epilogue(bias=bd, pw_w=wd, pw_x=xd, dact_z=dzd, dact="gelu"))
+            assert (ops.tensor_core_launches() - n0 == 2) == mode, "tensor-core kernel did not run when expected"
+            outs[mode] = (rel(z, z64), rel(y, y64), rel(yd, y64_d))
+    finally:
+        ops.set_tensor_core_mode(True)
+    for mode, errs in outs.items():
+        assert max(errs) < TOL, (mode, errs)
