@@ -25,7 +25,7 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
                       long pixels, const b2no_epilogue* e, cudaStream_t st);
 
 // operand images for the tensor-core tile kernel (tc_pointwise.cu): the last-dim inverse table as a
-// block-diagonal [128 x Ks] K-major matrix, hi then lo (3xTF32), ready to be copied into shared memory
+// block-diagonal row-major [128 x Ks] matrix, hi then lo (3xTF32); it becomes a TMEM-resident A operand
 struct b2no_tc_tables {
   float* timg;     // 2 * 128 * Ks floats, or nullptr when the geometry is not eligible
   int Ks, Qp, R;   // Ks = R * Qp, R = rows per 128-pixel tile, Qp = 2*K_last rounded up to 8

@@ -185,7 +185,7 @@ extern "C" int b2no_plan_create(const b2no_geom* g, b2no_plan** out) {
           float v = 0.f;
           if (r == m / Wd && q < 2 * K) v = tab[(size_t)q * npad + (m % Wd)];
           const float hi = tf32_round_host(v);
-          const size_t off = ((size_t)(m >> 3) * (tt.Ks >> 2) * 128 + (size_t)(k >> 2) * 128 + (m & 7) * 16 + (k & 3) * 4) / 4;
+          const size_t off = (size_t)m * tt.Ks + k;   // row-major: thread m of the converter loads row m into TMEM
           img[off] = hi;
           img[(size_t)128 * tt.Ks + off] = tf32_round_host(v - hi);
         }

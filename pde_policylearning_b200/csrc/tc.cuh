@@ -112,6 +112,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
   const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
   asm volatile(
@@ -148,6 +154,13 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn, int b_
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T      (one thread issues)

@@ -9,18 +9,22 @@
 // accumulate into the SAME TMEM tile, so the FNO layer (spectral_convolution.py:342-345 + fno_block.py:131-150),
 // the RNO FourierLayer2d (rno.py:224-228) and their dx adjoints are one pass over HBM: read x once, write y once.
 //
-// fp32 parity on tf32 tensor cores: every product is issued three times (3xTF32): x_hi*w_hi + x_lo*w_hi +
-// x_hi*w_lo, where x_hi is the raw fp32 tile exactly as TMA delivered it (the tensor core ignores the low 13
-// mantissa bits -- measured, tools/tc_probe.cu) and x_lo = x - trunc(x) is produced by an elementwise pass over
-// the tile in shared memory.  Measured error of the scheme: 4e-7 relative (probe T5).
+// Operand placement (measured on B200): feeding the pixel tile to the tensor core from shared
+// memory costs one 4 KB A-read per MMA and made the MMAs the bottleneck, so the A operands live in TMEM:
+//   - X tile: TMA box [C x 128 px] -> shared memory -> converter warps (thread = pixel) -> tcgen05.st as
+//     K-major A [128 lanes x C columns], hi (raw fp32; the tensor core reads only the upper 19 bits) and
+//     lo = rna_tf32(x - trunc(x));
+//   - T (block-diagonal last-dim inverse table, constant): loaded into TMEM once per CTA, hi and lo;
+//   - B operands (1x1 weights, A' rows) stay in shared memory, K-major no-swizzle core-matrix layout.
+// fp32 parity: every product is issued three times (3xTF32: hi*hi + lo*hi + hi*lo), error 4e-7 (tools/tc_probe.cu).
 //
-// Warp roles (448 threads, persistent CTAs, static round-robin tile schedule):
-//   warp 0      TMA producer: X tiles as MN-major operands (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B boxes of
-//               32 px x C rows), A' rows with cp.async.bulk
-//   warp 1      MMA issuer (one lane): tcgen05.mma.kind::tf32, tcgen05.commit -> mbarriers
-//   warps 2-5   converter: lo tiles
-//   warps 6-13  two epilogue groups alternating over the two TMEM accumulators: tcgen05.ld -> bias/act ->
-//               coalesced global stores (a warp writes 128 B per output channel)
+// Warp roles (448 threads, persistent CTAs, each CTA owns a contiguous run of tiles):
+//   warp 0      TMA producer (X boxes, cp.async.bulk for the A' rows), S-deep mbarrier ring
+//   warp 1      MMA issuer (one lane): tcgen05.mma.kind::tf32 TS form, tcgen05.commit -> mbarriers
+//   warps 2-5   converter: shared memory -> TMEM A operand (double buffered)
+//   warps 6-13  epilogue: all eight warps work on each tile (4 lane quadrants x 2 column halves),
+//               tcgen05.ld -> bias/act -> coalesced global stores (a warp writes 128 B per output channel);
+//               two TMEM accumulators so the MMAs of tile i+1 overlap the epilogue of tile i
 #include <stdlib.h>
 #include <string.h>
 
@@ -36,44 +40,49 @@ constexpr int kThreads = 448;
 struct PwTc {
   int B, Co, Np, C1, C1p, C2, C2p, Ks, Qp, R, S;
   int tiles_per_img;
-  long tiles, P;
+  long tiles, tiles_per_cta, P;
   const float* w1; int w1_t;
   const float* w2; int w2_t;
   const float* ahi; const float* alo; const float* timg;
   const float* bias; const float* add; const float* mul; const float* dz;
   float* preact; float* y;
   int act, dact;
+  int debug;          // bit0 no stores, bit1 no MMAs
 };
 
 struct PwLayout {
-  uint32_t w1h, w1l, w2h, w2l, th, tl, stages, stage_bytes, x1lo, x2, x2lo, ah, al, bars, total;
+  uint32_t w1h, w1l, w2h, w2l, bias, stages, stage_bytes, x2, ah, al, bars, total;
 };
 
 __host__ __device__ inline PwLayout pw_layout(const PwTc& p) {
   PwLayout L;
-  const uint32_t wb1 = (uint32_t)p.Np * p.C1p * 4, wb2 = (uint32_t)p.Np * p.C2p * 4, tb = 128u * p.Ks * 4;
+  const uint32_t wb1 = (uint32_t)p.Np * p.C1p * 4, wb2 = (uint32_t)p.Np * p.C2p * 4;
   const uint32_t xb1 = (uint32_t)p.C1p * 512, xb2 = (uint32_t)p.C2p * 512, ab = (uint32_t)p.Ks * p.Np * 4;
   uint32_t o = 0;
   L.w1h = o; o += wb1; L.w1l = o; o += wb1;
   L.w2h = o; o += wb2; L.w2l = o; o += wb2;
-  L.th = o; o += tb; L.tl = o; o += tb;
+  L.bias = o; o += (uint32_t)p.Np * 4;
   o = (o + 1023u) & ~1023u;
   L.stages = o;
-  L.x1lo = xb1; L.x2 = 2 * xb1; L.x2lo = 2 * xb1 + xb2; L.ah = 2 * xb1 + 2 * xb2; L.al = L.ah + ab;
+  L.x2 = xb1; L.ah = xb1 + xb2; L.al = L.ah + ab;
   L.stage_bytes = (L.al + ab + 1023u) & ~1023u;
   o += L.stage_bytes * p.S;
   L.bars = o;
-  o += 8 * (3 * p.S + 4) + 16;
+  o += 8 * (2 * p.S + 8) + 16;
   L.total = o + 1024;  // slack for the manual 1024-byte alignment of the dynamic window
   return L;
 }
 
+__host__ __device__ inline uint32_t pw_tmem_cols(const PwTc& p) {
+  return 2u * p.Np + 2u * p.Ks + 4u * (p.C1p + p.C2p);
+}
+
+// MODE 1: no activation;  2: GELU;  3: multiply by GELU'(dz);  0: generic (runtime act / dact, add, mul)
 template <int MODE>
 __device__ __forceinline__ float epi_value(float z, float mulv, float dzv, int act, int dact) {
-  // MODE 1: no activation, no dact;  2: GELU;  3: multiply by GELU'(dz);  0: generic
-  if (MODE == 1) return z * mulv;
-  if (MODE == 2) return b2no_act(z, B2NO_ACT_GELU) * mulv;
-  if (MODE == 3) return z * mulv * b2no_act_grad(dzv, B2NO_ACT_GELU);
+  if (MODE == 1) return z;
+  if (MODE == 2) return b2no_act(z, B2NO_ACT_GELU);
+  if (MODE == 3) return z * b2no_act_grad(dzv, B2NO_ACT_GELU);
   float v = b2no_act(z, act) * mulv;
   if (dact) v *= b2no_act_grad(dzv, dact);
   return v;
@@ -86,17 +95,18 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const PwLayout L = pw_layout(p);
   uint64_t* full = (uint64_t*)(smem + L.bars);
-  uint64_t* cvt = full + p.S;
-  uint64_t* empty = cvt + p.S;
-  uint64_t* acc_full = empty + p.S;
+  uint64_t* empty = full + p.S;
+  uint64_t* a_full = empty + p.S;
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* acc_full = a_empty + 2;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tslot = (uint32_t*)(acc_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint32_t ncols = 32;
-  while (ncols < 2u * p.Np) ncols <<= 1;
+  while (ncols < pw_tmem_cols(p)) ncols <<= 1;
 
-  // ---- one-time setup: weights (hi/lo, K-major core-matrix layout), spectral T image, barriers, TMEM ----
+  // ---- one-time setup: weights (hi/lo, K-major core-matrix layout), bias, barriers, TMEM ----
   for (int i = tid; i < p.Np * p.C1p; i += kThreads) {
     const int n = i / p.C1p, k = i - n * p.C1p;
     float w = 0.f;
@@ -113,10 +123,13 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
     *(float*)(smem + L.w2h + kmajor_off(n, k, p.C2p)) = hi;
     *(float*)(smem + L.w2l + kmajor_off(n, k, p.C2p)) = tf32_rna(w - hi);
   }
-  for (int i = tid; i < 2 * 128 * p.Ks; i += kThreads) ((float*)(smem + L.th))[i] = p.timg[i];
+  for (int i = tid; i < p.Np; i += kThreads) ((float*)(smem + L.bias))[i] = (p.bias && i < p.Co) ? p.bias[i] : 0.f;
   if (tid == 0) {
-    for (int s = 0; s < p.S; s++) { mbar_init(&full[s], 1); mbar_init(&cvt[s], 128); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+    for (int s = 0; s < p.S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(&a_full[a], 128); mbar_init(&a_empty[a], 1);
+      mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 256);
+    }
     fence_barrier_init();
   }
   fence_proxy_async();
@@ -126,15 +139,20 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = *tslot;
+  const uint32_t t_hi = tbase + 2u * p.Np, t_lo = t_hi + p.Ks;
+  const uint32_t a_base = t_lo + p.Ks, a_width = 2u * (p.C1p + p.C2p);
 
   const uint32_t xb1 = (uint32_t)p.C1p * 512, xb2 = (uint32_t)p.C2p * 512, ab = (uint32_t)p.Ks * p.Np * 4;
+  // each CTA owns a contiguous run of tiles (sequential DRAM pages per channel row, same sample for A')
+  const long t_first = (long)blockIdx.x * p.tiles_per_cta;
+  const long t_end = t_first + p.tiles_per_cta < p.tiles ? t_first + p.tiles_per_cta : p.tiles;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       const uint32_t bytes = xb1 + xb2 + 2 * ab;
       int it = 0;
-      for (long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, it++) {
+      for (long tile = t_first; tile < t_end; tile++, it++) {
         const int s = it % p.S;
         const uint32_t ph = (uint32_t)(it / p.S) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
@@ -142,13 +160,10 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
         uint8_t* st = smem + L.stages + (size_t)s * L.stage_bytes;
         const int b = (int)(tile / p.tiles_per_img);
         const int t_in_img = (int)(tile - (long)b * p.tiles_per_img);
-        const int p0 = t_in_img * 128;
-        for (int j = 0; j < 4; j++) tma_load_3d(st + j * (xb1 / 4), &tm1, &full[s], p0 + 32 * j, 0, b);
-        if (p.C2p)
-          for (int j = 0; j < 4; j++) tma_load_3d(st + L.x2 + j * (xb2 / 4), &tm2, &full[s], p0 + 32 * j, 0, b);
+        tma_load_3d(st, &tm1, &full[s], t_in_img * 128, 0, b);
+        if (p.C2p) tma_load_3d(st + L.x2, &tm2, &full[s], t_in_img * 128, 0, b);
         if (p.Ks) {
-          const size_t row0 = ((size_t)b * p.tiles_per_img + t_in_img) * p.R;
-          const size_t off = row0 * (size_t)p.Qp * p.Np;
+          const size_t off = (size_t)tile * p.R * p.Qp * p.Np;
           bulk_load(st + L.ah, p.ahi + off, ab, &full[s]);
           bulk_load(st + L.al, p.alo + off, ab, &full[s]);
         }
@@ -156,129 +171,191 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t id_x = idesc_tf32(128, p.Np, 1, 0), id_t = idesc_tf32(128, p.Np, 0, 0);
+    // The whole warp runs the loop with warp-uniform values (descriptors stay in uniform registers); one
+    // elected lane issues the tcgen05 instructions.
+    {
+      const uint32_t idesc = idesc_tf32(128, p.Np, 0, 0);
       const uint32_t sbase = smem_u32(smem);
       const uint64_t d_w1h = smem_desc(sbase + L.w1h, 128, (p.C1p / 4) * 128, LAYOUT_NONE);
       const uint64_t d_w1l = smem_desc(sbase + L.w1l, 128, (p.C1p / 4) * 128, LAYOUT_NONE);
       const uint64_t d_w2h = smem_desc(sbase + L.w2h, 128, (p.C2p / 4) * 128, LAYOUT_NONE);
       const uint64_t d_w2l = smem_desc(sbase + L.w2l, 128, (p.C2p / 4) * 128, LAYOUT_NONE);
-      const uint64_t d_th = smem_desc(sbase + L.th, 128, (p.Ks / 4) * 128, LAYOUT_NONE);
-      const uint64_t d_tl = smem_desc(sbase + L.tl, 128, (p.Ks / 4) * 128, LAYOUT_NONE);
       const uint32_t lbo_a = (uint32_t)(p.Np / 8) * 128;
+      const bool nomma = (p.debug & 2) != 0;
       int it = 0;
-      for (long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, it++) {
+      for (long tile = t_first; tile < t_end; tile++, it++) {
         const int s = it % p.S;
         const uint32_t ph = (uint32_t)(it / p.S) & 1u;
         const int a = it & 1;
         const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(&full[s], ph);
-        mbar_wait(&cvt[s], ph);
+        mbar_wait(&full[s], ph);         // A' rows landed (and X, consumed by the converter)
+        mbar_wait(&a_full[a], aph);      // converter filled TMEM A buffer a
         mbar_wait(&acc_empty[a], aph ^ 1u);
         tc_fence_after();
         const uint32_t st = sbase + L.stages + (uint32_t)s * L.stage_bytes;
         const uint32_t d = tbase + (uint32_t)a * p.Np;
+        const uint32_t xa = a_base + (uint32_t)a * a_width;
         uint32_t acc = 0;
-        // MN-major X operand: atom = 4 channel rows x 128 B (SBO 512); 32-px groups C*128 B apart (LBO)
-        const uint64_t d_x1 = smem_desc(st, p.C1p * 128, 512, LAYOUT_SW128_32B);
-        const uint64_t d_x1lo = smem_desc(st + L.x1lo, p.C1p * 128, 512, LAYOUT_SW128_32B);
-        for (int pass = 0; pass < 3; pass++) {
-          const uint64_t dx = pass == 1 ? d_x1lo : d_x1;
-          const uint64_t dw = pass == 2 ? d_w1l : d_w1h;
-          for (int k = 0; k < p.C1p / 8; k++) {
-            mma_tf32_ss(d, dx + (uint64_t)(k * 64), dw + (uint64_t)(k * 16), id_x, acc);
-            acc = 1;
-          }
-        }
-        if (p.C2p) {
-          const uint64_t d_x2 = smem_desc(st + L.x2, p.C2p * 128, 512, LAYOUT_SW128_32B);
-          const uint64_t d_x2lo = smem_desc(st + L.x2lo, p.C2p * 128, 512, LAYOUT_SW128_32B);
+        if (!nomma && elect_one()) {
           for (int pass = 0; pass < 3; pass++) {
-            const uint64_t dx = pass == 1 ? d_x2lo : d_x2;
-            const uint64_t dw = pass == 2 ? d_w2l : d_w2h;
-            for (int k = 0; k < p.C2p / 8; k++) mma_tf32_ss(d, dx + (uint64_t)(k * 64), dw + (uint64_t)(k * 16), id_x, 1);
+            const uint32_t ac = pass == 1 ? xa + p.C1p : xa;
+            const uint64_t dw = pass == 2 ? d_w1l : d_w1h;
+            for (int k = 0; k < p.C1p / 8; k++) {
+              mma_tf32_ts(d, ac + 8 * k, dw + (uint64_t)(k * 16), idesc, acc);
+              acc = 1;
+            }
+          }
+          if (p.C2p) {
+            const uint32_t x2 = xa + 2 * p.C1p;
+            for (int pass = 0; pass < 3; pass++) {
+              const uint32_t ac = pass == 1 ? x2 + p.C2p : x2;
+              const uint64_t dw = pass == 2 ? d_w2l : d_w2h;
+              for (int k = 0; k < p.C2p / 8; k++) mma_tf32_ts(d, ac + 8 * k, dw + (uint64_t)(k * 16), idesc, 1);
+            }
+          }
+          if (p.Ks) {
+            // B operand A'[n = channel][k = (row, q)]: K-chunks outermost (LBO = Np/8 * 128), channel groups 128 B apart
+            const uint64_t d_ah = smem_desc(st + L.ah, lbo_a, 128, LAYOUT_NONE);
+            const uint64_t d_al = smem_desc(st + L.al, lbo_a, 128, LAYOUT_NONE);
+            for (int pass = 0; pass < 3; pass++) {
+              const uint32_t tcn = pass == 1 ? t_lo : t_hi;
+              const uint64_t da = pass == 2 ? d_al : d_ah;
+              for (int k = 0; k < p.Ks / 8; k++)
+                mma_tf32_ts(d, tcn + 8 * k, da + (uint64_t)(k * (2 * lbo_a / 16)), idesc, 1);
+            }
           }
         }
-        if (p.Ks) {
-          // B operand A'[n = channel][k = (row, q)]: K-chunks outermost (LBO = Np/8 * 128), channel groups 128 B apart
-          const uint64_t d_ah = smem_desc(st + L.ah, lbo_a, 128, LAYOUT_NONE);
-          const uint64_t d_al = smem_desc(st + L.al, lbo_a, 128, LAYOUT_NONE);
-          for (int pass = 0; pass < 3; pass++) {
-            const uint64_t dt = pass == 1 ? d_tl : d_th;
-            const uint64_t da = pass == 2 ? d_al : d_ah;
-            for (int k = 0; k < p.Ks / 8; k++)
-              mma_tf32_ss(d, dt + (uint64_t)(k * 16), da + (uint64_t)(k * (2 * lbo_a / 16)), id_t, 1);
-          }
+        if (elect_one()) {
+          mma_commit(&empty[s]);
+          mma_commit(&a_empty[a]);
+          mma_commit(&acc_full[a]);
         }
-        mma_commit(&empty[s]);
-        mma_commit(&acc_full[a]);
+        __syncwarp();
       }
     }
   } else if (warp < 6) {
-    // ===================== converter: lo tiles =====================
-    const int ct = tid - 64;
+    // ===================== converter: shared memory -> TMEM A operand (thread = pixel = TMEM lane) =====================
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    // constant T operand, once
+    for (int c0 = 0; c0 < p.Ks; c0 += 8) {
+      float hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        hi[j] = __ldg(p.timg + (size_t)m * p.Ks + c0 + j);
+        lo[j] = __ldg(p.timg + (size_t)128 * p.Ks + (size_t)m * p.Ks + c0 + j);
+      }
+      tmem_st8(t_hi + lane_base + c0, hi);
+      tmem_st8(t_lo + lane_base + c0, lo);
+    }
     int it = 0;
-    for (long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, it++) {
+    for (long tile = t_first; tile < t_end; tile++, it++) {
       const int s = it % p.S;
       const uint32_t ph = (uint32_t)(it / p.S) & 1u;
+      const int a = it & 1;
+      const uint32_t aph = (uint32_t)(it >> 1) & 1u;
       mbar_wait(&full[s], ph);
-      uint8_t* st = smem + L.stages + (size_t)s * L.stage_bytes;
-      const float4* src = (const float4*)st;
-      float4* dst = (float4*)(st + L.x1lo);
-      for (int i = ct; i < p.C1p * 32; i += 128) {
-        const float4 x = src[i];
-        dst[i] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+      mbar_wait(&a_empty[a], aph ^ 1u);
+      tc_fence_after();
+      const float* sx = (const float*)(smem + L.stages + (size_t)s * L.stage_bytes);
+      const uint32_t xa = a_base + (uint32_t)a * a_width + lane_base;
+      for (int c0 = 0; c0 < p.C1p; c0 += 8) {
+        float hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          hi[j] = sx[(c0 + j) * 128 + m];
+          lo[j] = tf32_lo(hi[j]);
+        }
+        tmem_st8(xa + c0, hi);
+        tmem_st8(xa + p.C1p + c0, lo);
       }
       if (p.C2p) {
-        src = (const float4*)(st + L.x2);
-        dst = (float4*)(st + L.x2lo);
-        for (int i = ct; i < p.C2p * 32; i += 128) {
-          const float4 x = src[i];
-          dst[i] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+        const float* sx2 = (const float*)((const uint8_t*)sx + L.x2);
+        for (int c0 = 0; c0 < p.C2p; c0 += 8) {
+          float hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            hi[j] = sx2[(c0 + j) * 128 + m];
+            lo[j] = tf32_lo(hi[j]);
+          }
+          tmem_st8(xa + 2 * p.C1p + c0, hi);
+          tmem_st8(xa + 2 * p.C1p + p.C2p + c0, lo);
         }
       }
-      fence_proxy_async();
-      mbar_arrive(&cvt[s]);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&a_full[a]);
     }
   } else {
-    // ===================== epilogue (two groups, one per accumulator) =====================
-    const int g = (warp - 6) >> 2;
+    // ===================== epilogue: 8 warps per tile = 4 lane quadrants x 2 column halves =====================
+    const int half = (warp - 6) >> 2;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int t = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    for (int it = g;; it += 2) {
-      const long tile = (long)blockIdx.x + (long)it * gridDim.x;
-      if (tile >= p.tiles) break;
+    const float* sbias = (const float*)(smem + L.bias);
+    const bool nostore = (p.debug & 1) != 0;
+    int it = 0;
+    for (long tile = t_first; tile < t_end; tile++, it++) {
+      const int a = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
       const int b = (int)(tile / p.tiles_per_img);
       const long px = (tile - (long)b * p.tiles_per_img) * 128 + t;
       const size_t base = (size_t)b * p.Co * p.P + px;
-      mbar_wait(&acc_full[g], aph);
+      mbar_wait(&acc_full[a], aph);
       tc_fence_after();
-      for (int c0 = 0; c0 < p.Co; c0 += 16) {
-        float v[16], av[16], mv[16], dv[16];
-        tmem_ld16(tbase + lane_base + (uint32_t)(g * p.Np + c0), v);
+      for (int c0 = half * 16; c0 < p.Co; c0 += 32) {
+        float v[16];
+        tmem_ld16(tbase + lane_base + (uint32_t)(a * p.Np + c0), v);
+        if (MODE == 0) {
+          float av[16], mv[16], dv[16];
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-          const bool ok = c0 + j < p.Co;
-          const size_t idx = base + (size_t)(c0 + j) * p.P;
-          av[j] = (p.add && ok) ? __ldg(p.add + idx) : 0.f;
-          mv[j] = (p.mul && ok) ? __ldg(p.mul + idx) : 1.f;
-          dv[j] = (p.dz && ok) ? __ldg(p.dz + idx) : 0.f;
-        }
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; j++) {
-          if (c0 + j < p.Co) {
+          for (int j = 0; j < 16; j++) {
+            const bool ok = c0 + j < p.Co;
             const size_t idx = base + (size_t)(c0 + j) * p.P;
-            const float z = v[j] + (p.bias ? __ldg(p.bias + c0 + j) : 0.f) + av[j];
-            if (p.preact) p.preact[idx] = z;
-            p.y[idx] = epi_value<MODE>(z, mv[j], dv[j], p.act, p.dact);
+            av[j] = (p.add && ok) ? __ldg(p.add + idx) : 0.f;
+            mv[j] = (p.mul && ok) ? __ldg(p.mul + idx) : 1.f;
+            dv[j] = (p.dz && ok) ? __ldg(p.dz + idx) : 0.f;
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            if (c0 + j < p.Co) {
+              const size_t idx = base + (size_t)(c0 + j) * p.P;
+              const float z = v[j] + sbias[c0 + j] + av[j];
+              if (p.preact) p.preact[idx] = z;
+              const float r = epi_value<0>(z, mv[j], dv[j], p.act, p.dact);
+              if (!nostore) p.y[idx] = r;
+            }
+          }
+        } else {
+          float dv[16];
+          if (MODE == 3) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) dv[j] = (c0 + j < p.Co) ? __ldg(p.dz + base + (size_t)(c0 + j) * p.P) : 0.f;
+          }
+          float bv[16];
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(bv + j) = *reinterpret_cast<const float4*>(sbias + c0 + j);
+          tmem_ld_wait();
+          float* yp = p.y + base + (size_t)c0 * p.P;
+          if (MODE == 2 && p.preact) {
+            float* zp = p.preact + base + (size_t)c0 * p.P;
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+              if (c0 + j < p.Co) zp[(size_t)j * p.P] = v[j] + bv[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            if (c0 + j < p.Co) {
+              const float r = epi_value<MODE>(v[j] + bv[j], 1.f, MODE == 3 ? dv[j] : 0.f, 0, 0);
+              if (!nostore) yp[(size_t)j * p.P] = r;
+            }
           }
         }
       }
       tc_fence_before();
-      mbar_arrive(&acc_empty[g]);
+      mbar_arrive(&acc_empty[a]);
     }
   }
   tc_fence_before();
@@ -288,25 +365,37 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
 
 // A'[b][row][q/4][n/8][n%8][q%4] (hi and lo) from the kept spectrum: the second-to-last inverse stage.
 //   S[b,o,h,ky] = sum_kx M[kx][h] * spec[b][o][kx][ky];   q = 2 ky -> Re S, 2 ky + 1 -> Im S
+// One block per (sample, group of HB rows): the sample's spectrum is staged in shared memory once.
+constexpr int kInvHB = 8;
 __global__ void __launch_bounds__(256)
 k_inv_h(const float2* __restrict__ spec, const float2* __restrict__ M, float* __restrict__ ahi, float* __restrict__ alo,
-        int B, int Co, int Np, int Kx, int H, int Ky, int Qp) {
+        int Co, int Np, int Kx, int H, int Ky, int Qp) {
+  extern __shared__ float2 s_spec[];  // [Co][Kx*Ky + 1]
+  const int b = blockIdx.y, h0 = blockIdx.x * kInvHB;
+  const int kk = Kx * Ky, stride = kk + 1;
+  const float2* sp = spec + (size_t)b * Co * kk;
+  for (int i = threadIdx.x; i < Co * kk; i += blockDim.x) {
+    const int o = i / kk, r = i - o * kk;
+    s_spec[o * stride + r] = sp[i];
+  }
+  __syncthreads();
   const int ng = Np >> 3, nq = Qp >> 2;
-  const long total = (long)B * H * nq * ng * 16;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int l0 = (int)(idx & 1), o8 = (int)((idx >> 1) & 7);
-    long r = idx >> 4;
-    const int og = (int)(r % ng); r /= ng;
-    const int kq = (int)(r % nq); r /= nq;
-    const int h = (int)(r % H);
-    const int b = (int)(r / H);
+  const int per_row = nq * ng * 16;
+  for (int idx = threadIdx.x; idx < kInvHB * per_row; idx += blockDim.x) {
+    const int hl = idx / per_row;
+    int r = idx - hl * per_row;
+    const int h = h0 + hl;
+    if (h >= H) break;
+    const int l0 = r & 1, o8 = (r >> 1) & 7;
+    r >>= 4;
+    const int og = r % ng, kq = r / ng;
     const int ky = kq * 2 + l0, o = og * 8 + o8;
     float sr = 0.f, si = 0.f;
     if (o < Co && ky < Ky) {
-      const float2* sp = spec + (((size_t)b * Co + o) * Kx) * Ky + ky;
+      const float2* so = s_spec + o * stride + ky;
       for (int kx = 0; kx < Kx; kx++) {
         const float2 m = __ldg(M + (size_t)kx * H + h);
-        const float2 v = __ldg(sp + (size_t)kx * Ky);
+        const float2 v = so[kx * Ky];
         sr = fmaf(m.x, v.x, fmaf(-m.y, v.y, sr));
         si = fmaf(m.x, v.y, fmaf(m.y, v.x, si));
       }
@@ -339,6 +428,7 @@ bool b2no_tc_available() {
 }
 
 extern "C" int64_t b2no_tensor_core_launches(void) { return g_tc_launches; }
+void b2no_tc_count_launch() { g_tc_launches++; }
 
 extern "C" int b2no_set_tensor_core_mode(int on) {
   g_tc_state = -1;
@@ -374,16 +464,16 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
     const int32_t* n = which == 0 ? plan->g.nout : plan->g.nin;
     if ((long)n[0] * n[1] != pixels) return B2NO_E_ARG;
     const size_t afl = (size_t)batch * n[0] * p.Qp * p.Np;
-    float* ahi = work;
-    float* alo = work + afl;
-    p.ahi = ahi; p.alo = alo;
+    p.ahi = work;
+    p.alo = work + afl;
   }
+  if (pw_tmem_cols(p) > 512) return 1;
   // shared-memory budget -> number of stages
   int dev = 0, max_smem = 0;
   B2NO_CHECK_CUDA(cudaGetDevice(&dev));
   B2NO_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   PwLayout L;
-  for (p.S = 4; p.S >= 2; p.S--) {
+  for (p.S = 6; p.S >= 2; p.S--) {
     L = pw_layout(p);
     if ((int)L.total <= max_smem) break;
   }
@@ -393,32 +483,39 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
   {
     uint64_t dims[3] = {(uint64_t)pixels, (uint64_t)p.C1, (uint64_t)batch};
     uint64_t str[3] = {4, (uint64_t)pixels * 4, (uint64_t)pixels * 4 * p.C1};
-    uint32_t box[3] = {32, (uint32_t)p.C1p, 1};
-    if (make_tmap_f32(&tm1, e->pw_x, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+    uint32_t box[3] = {128, (uint32_t)p.C1p, 1};
+    if (make_tmap_f32(&tm1, e->pw_x, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
     tm2 = tm1;
     if (has2) {
       uint64_t dims2[3] = {(uint64_t)pixels, (uint64_t)p.C2, (uint64_t)batch};
       uint64_t str2[3] = {4, (uint64_t)pixels * 4, (uint64_t)pixels * 4 * p.C2};
-      uint32_t box2[3] = {32, (uint32_t)p.C2p, 1};
-      if (make_tmap_f32(&tm2, e->pw2_x, 3, dims2, str2, box2, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+      uint32_t box2[3] = {128, (uint32_t)p.C2p, 1};
+      if (make_tmap_f32(&tm2, e->pw2_x, 3, dims2, str2, box2, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
     }
   }
   if (spec) {
     const int32_t* n = which == 0 ? plan->g.nout : plan->g.nin;
     const float2* M = which == 0 ? plan->m_inv[0] : plan->m_adjfwd[0];
-    const long total = (long)batch * n[0] * (p.Qp / 4) * (p.Np / 8) * 16;
-    long blocks = (total + 255) / 256;
-    const long cap = (long)b2no_sm_count() * 8;
-    if (blocks > cap) blocks = cap;
-    k_inv_h<<<(unsigned)blocks, 256, 0, st>>>((const float2*)spec, M, (float*)p.ahi, (float*)p.alo, batch, channels, p.Np,
-                                              plan->K[0], n[0], plan->K[1], p.Qp);
+    const size_t smem = (size_t)channels * (plan->K[0] * plan->K[1] + 1) * sizeof(float2);
+    if (smem > 200 * 1024) return 1;
+    if (smem > 48 * 1024) B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_inv_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((n[0] + kInvHB - 1) / kInvHB), (unsigned)batch);
+    k_inv_h<<<grid, 256, smem, st>>>((const float2*)spec, M, (float*)p.ahi, (float*)p.alo, channels, p.Np, plan->K[0], n[0],
+                                     plan->K[1], p.Qp);
     B2NO_LAUNCH_CHECK();
   }
+  const bool extras = p.add || p.mul;
   int mode = 0;
-  if (!p.dact && p.act == B2NO_ACT_NONE) mode = 1;
-  else if (!p.dact && p.act == B2NO_ACT_GELU) mode = 2;
-  else if (p.dact == B2NO_ACT_GELU && p.act == B2NO_ACT_NONE) mode = 3;
+  if (!extras && !p.dact && p.act == B2NO_ACT_NONE && !p.preact) mode = 1;
+  else if (!extras && !p.dact && p.act == B2NO_ACT_GELU) mode = 2;
+  else if (!extras && p.dact == B2NO_ACT_GELU && p.act == B2NO_ACT_NONE && !p.preact) mode = 3;
   long grid = p.tiles < b2no_sm_count() ? p.tiles : b2no_sm_count();
+  p.tiles_per_cta = (p.tiles + grid - 1) / grid;
+  grid = (p.tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  {
+    const char* dbg = getenv("B2NO_TC_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
 #define LAUNCH(M)                                                                                                  \
   do {                                                                                                             \
     B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_pw_tc<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));  \
