@@ -140,6 +140,16 @@ int b2no_pw_wgrad(const float* g, const float* x, float* dw, float* db, float* p
 int b2no_mlp_head_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                       float* out, int batch, int ci, int hidden, int64_t pixels, int b1_per_sample,
                       int act, void* stream);
+/* input-gradient half of the backward of the fused head (hidden activations recomputed on the tensor cores):
+ *   f[b,j,p] = g[b,p] w2[j] act'(z1[b,j,p]);  gx[b,i,p] = sum_j w1[j,i] f[b,j,p] (* dact'(dact_z) when given);
+ *   dw2[j] = sum_{b,p} g[b,p] act(z1[b,j,p]);  gz (optional, (batch, hidden, pixels)) receives f for b2no_pw_wgrad.
+ * partial: b2no_mlp_head_bwd_scratch_floats(hidden) floats.  Returns B2NO_E_UNSUPPORTED when the shape has no
+ * tensor-core kernel (the caller then composes the pointwise entry points). */
+int64_t b2no_mlp_head_bwd_scratch_floats(int hidden);
+int b2no_mlp_head_bwd_supported(int ci, int hidden, int64_t pixels);
+int b2no_mlp_head_bwd(const float* x, const float* w1, const float* b1, const float* w2, const float* g, float* gx,
+                      float* gz, float* dw2, float* partial, int batch, int ci, int hidden, int64_t pixels,
+                      int b1_per_sample, int act, const float* dact_z, int dact, void* stream);
 /* RNO gate (rno.py:259): h_next = (1 - z) * h + z2 * hhat, and its backward */
 int b2no_rno_gate_fwd(const float* z, const float* z2, const float* hhat, const float* h, float* out,
                       int64_t n, void* stream);

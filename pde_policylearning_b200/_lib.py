@@ -11,7 +11,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2no.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["plan.cu", "spectral.cu", "pointwise.cu", "tc_pointwise.cu"]
+SOURCES = ["plan.cu", "spectral.cu", "pointwise.cu", "tc_pointwise.cu", "tc_wgrad.cu", "tc_mlp.cu"]
 
 MAX_DIM = 3
 NORM = {"backward": 0, "forward": 1, "ortho": 2}
@@ -90,6 +90,10 @@ def lib():
     L.b2no_pw_wgrad_scratch_floats.argtypes = [i32, i32]
     L.b2no_pw_wgrad.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i64, vp]
     L.b2no_mlp_head_fwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i64, i32, i32, vp]
+    L.b2no_mlp_head_bwd_supported.argtypes = [i32, i32, i64]
+    L.b2no_mlp_head_bwd_scratch_floats.restype = i64
+    L.b2no_mlp_head_bwd_scratch_floats.argtypes = [i32]
+    L.b2no_mlp_head_bwd.argtypes = [vp] * 9 + [i32, i32, i32, i64, i32, i32, vp, i32, vp]
     L.b2no_rno_gate_fwd.argtypes = [vp, vp, vp, vp, vp, i64, vp]
     L.b2no_rno_gate_bwd.argtypes = [vp] * 9 + [i64, vp]
     L.b2no_rel_l2_sums.argtypes = [vp, vp, vp, i32, i64, vp]
@@ -107,7 +111,7 @@ EXPORTS = [
     "b2no_plan_create", "b2no_plan_destroy", "b2no_plan_kept", "b2no_plan_workspace_floats",
     "b2no_set_tensor_core_mode", "b2no_tensor_core_launches",
     "b2no_dft_forward", "b2no_dft_inverse", "b2no_mix", "b2no_mix_dw",
-    "b2no_act_bwd", "b2no_pw_wgrad_scratch_floats", "b2no_pw_wgrad", "b2no_mlp_head_fwd",
+    "b2no_act_bwd", "b2no_pw_wgrad_scratch_floats", "b2no_pw_wgrad", "b2no_mlp_head_fwd", "b2no_mlp_head_bwd_scratch_floats", "b2no_mlp_head_bwd_supported", "b2no_mlp_head_bwd",
     "b2no_rno_gate_fwd", "b2no_rno_gate_bwd", "b2no_rel_l2_sums", "b2no_rel_l2_bwd",
 ]
 

@@ -195,6 +195,18 @@ extern "C" int b2no_pw_wgrad(const float* g, const float* x, float* dw, float* d
   if (!g || !x || !dw || !partial || batch < 1 || ci < 1 || co < 1 || pixels < 1) return B2NO_E_ARG;
   if (ci > 1024) return B2NO_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    // tensor-core path (tc_wgrad.cu) when eligible: per-CTA partials, same deterministic reduction
+    int nblk = 0;
+    const int rc = b2no_tc_wgrad(g, x, partial, wgrad_blocks_x(), batch, ci, co, pixels, &nblk, st);
+    if (rc == 0) {
+      const int n = co * ci + co;
+      k_pw_wgrad_reduce<<<(n + 255) / 256, 256, 0, st>>>(partial, dw, db, nblk, ci, co);
+      B2NO_LAUNCH_CHECK();
+      return 0;
+    }
+    if (rc != 1) return rc;
+  }
   int tiles_i, tiles_o, opb, gy;
   wgrad_cfg(ci, co, &tiles_i, &tiles_o, &opb, &gy);
   const int nt = tiles_o * tiles_i;
@@ -298,6 +310,11 @@ extern "C" int b2no_mlp_head_fwd(const float* x, const float* w1, const float* b
                                  int b1_per_sample, int act, void* stream) {
   if (!x || !w1 || !w2 || !out || batch < 1 || hidden < 1 || pixels < 1) return B2NO_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    // tensor-core fused MLP (tc_mlp.cu) when eligible
+    const int rc = b2no_tc_mlp_fwd(x, w1, b1, w2, b2, out, batch, ci, hidden, 1, pixels, b1_per_sample, act, st);
+    if (rc != 1) return rc;
+  }
   switch (ci) {
     case 8: return launch_head<8>(x, w1, b1, w2, b2, out, batch, hidden, pixels, b1_per_sample, act, st);
     case 16: return launch_head<16>(x, w1, b1, w2, b2, out, batch, hidden, pixels, b1_per_sample, act, st);

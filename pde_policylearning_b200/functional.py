@@ -8,6 +8,7 @@ The math is SURVEY.md 8a.0 (verified against the reference by oracle/closed_form
 """
 from __future__ import annotations
 
+import math
 from typing import List, Optional, Sequence
 
 import torch
@@ -189,11 +190,57 @@ def pointwise_conv2(x, weight, bias, act, x2, weight2):
     return PointwiseConv2Fn.apply(x, weight, bias, act, x2, weight2)
 
 
+class MlpHeadFn(torch.autograd.Function):
+    """out = b2 + w2 . act(W1 x + b1), out_channels == 1 (tfno.py:34-38, pinobserver.py:230-232, rno.py:170-174).
+    The hidden tensor is never stored: the backward recomputes it on the tensor cores (csrc/tc_mlp.cu), emits
+    gx and dw2 directly and writes gz = g w2 act'(z1) once for the weight-gradient kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, act):
+        ops._require_cuda(x)
+        x = _contig(x.float())
+        w1m = _contig(w1.detach().reshape(w1.shape[0], -1).float())
+        w2v = _contig(w2.detach().reshape(-1).float())
+        b1c = None if b1 is None else _contig(b1.detach().float())
+        out = ops.mlp_head_fwd(x, w1m, b1c, w2v, None if b2 is None else _contig(b2.detach().float()), act)
+        ctx.act = act
+        ctx.shapes = (tuple(w1.shape), None if b1 is None else tuple(b1.shape), tuple(w2.shape),
+                      None if b2 is None else tuple(b2.shape))
+        ctx.save_for_backward(x, w1m, b1c, w2v)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w1m, b1c, w2v = ctx.saved_tensors
+        g = _contig(g.float())
+        need_x, need_w1, need_b1, need_w2, need_b2 = ctx.needs_input_grad[:5]
+        res = ops.mlp_head_bwd(x, w1m, b1c, w2v, g, ctx.act, want_gz=need_w1 or need_b1)
+        if res is None:
+            raise RuntimeError("mlp_head backward: shape lost its tensor-core kernel between forward and backward")
+        gx, gz, dw2 = res
+        dw1 = db1 = None
+        if need_w1 or need_b1:
+            per_sample = b1c is not None and b1c.dim() == 2
+            dw1, db1 = ops.pw_wgrad(gz, x, need_bias=need_b1 and not per_sample)
+            dw1 = dw1.reshape(ctx.shapes[0])
+            if need_b1 and per_sample:
+                db1 = gz.sum(dim=tuple(range(2, gz.dim())))
+            if db1 is not None:
+                db1 = db1.reshape(ctx.shapes[1])
+        db2 = g.sum().reshape(ctx.shapes[3]) if need_b2 else None
+        return (gx if need_x else None, dw1 if need_w1 else None, db1 if need_b1 else None,
+                dw2.reshape(ctx.shapes[2]) if need_w2 else None, db2, None)
+
+
 def mlp_head(x, w1, b1, w2, b2, act="gelu"):
-    """Projection head Ci -> hidden -> act -> 1 (tfno.py:34-38).  Without autograd the fused kernel never
-    materialises the hidden tensor; with autograd it is two pointwise convs (hidden saved for backward)."""
+    """Projection head Ci -> hidden -> act -> 1 (tfno.py:34-38).  The fused kernels never materialise the hidden
+    tensor in the forward; shapes without a fused kernel compose two pointwise convs (hidden saved for backward)."""
     needs_grad = torch.is_grad_enabled() and any(
         t is not None and t.requires_grad for t in (x, w1, b1, w2, b2))
+    if (needs_grad and x.is_cuda and w2.reshape(-1, w1.shape[0]).shape[0] == 1 and (b1 is None or b1.dim() <= 2)
+            and ops.mlp_head_bwd_supported(x.shape[1], w1.shape[0], math.prod(x.shape[2:]))
+            and x.data_ptr() % 16 == 0):
+        return MlpHeadFn.apply(x, w1, b1, w2, b2, act)
     if (not needs_grad and w2.reshape(-1, w1.shape[0]).shape[0] == 1 and x.shape[1] in (8, 16, 32, 64)
             and (b1 is None or b1.dim() <= 2)):
         return ops.mlp_head_fwd(_contig(x.float()), _contig(w1.reshape(w1.shape[0], -1).float()),

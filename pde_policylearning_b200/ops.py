@@ -291,6 +291,33 @@ def mlp_head_fwd(x, w1, b1, w2, b2, act="gelu") -> torch.Tensor:
     return out
 
 
+def mlp_head_bwd_supported(ci: int, hidden: int, pixels: int) -> bool:
+    return bool(_lib.lib().b2no_mlp_head_bwd_supported(ci, hidden, pixels))
+
+
+def mlp_head_bwd(x, w1, b1, w2, g, act="gelu", want_gz=True, dact_z=None, dact=None):
+    """Fused backward (input-gradient half) of the Ci -> hidden -> act -> 1 head.  Returns (gx, gz | None, dw2) or
+    None when the shape has no tensor-core kernel."""
+    B, ci = x.shape[:2]
+    grid = tuple(x.shape[2:])
+    hidden = w1.shape[0]
+    P = math.prod(grid)
+    L = _lib.lib()
+    per_sample = b1 is not None and b1.dim() == 2
+    gx = torch.empty_like(x)
+    gz = torch.empty((B, hidden) + grid, dtype=torch.float32, device=x.device) if want_gz else None
+    dw2 = torch.empty((hidden,), dtype=torch.float32, device=x.device)
+    partial = torch.empty(int(L.b2no_mlp_head_bwd_scratch_floats(hidden)), dtype=torch.float32, device=x.device)
+    rc = L.b2no_mlp_head_bwd(_ptr(x), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(g), _ptr(gx), _ptr(gz), _ptr(dw2), _ptr(partial),
+                             B, ci, hidden, P, 1 if per_sample else 0, ACT[act], _ptr(dact_z),
+                             ACT[dact] if dact_z is not None else 0, _stream())
+    if rc == -2:
+        return None
+    check(rc, "mlp_head_bwd")
+    LAUNCHES[0] += 2
+    return gx, gz, dw2
+
+
 def rno_gate_fwd(z, z2, hh, h):
     out = torch.empty_like(h)
     check(_lib.lib().b2no_rno_gate_fwd(_ptr(z), _ptr(z2), _ptr(hh), _ptr(h), _ptr(out), h.numel(), _stream()), "gate")

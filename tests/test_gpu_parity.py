@@ -442,3 +442,57 @@ def test_tensor_core_tile_kernel(case):
         ops.set_tensor_core_mode(True)
     for mode, errs in outs.items():
         assert max(errs) < TOL, (mode, errs)
+
+
+@pytest.mark.parametrize("case", [(2, 32, 32, (128, 128)), (1, 256, 32, (128, 64)), (3, 20, 3, (32, 32)), (2, 34, 34, (32, 32)),
+                                  (1, 136, 40, (16, 16, 8))], ids=str)
+def test_tensor_core_wgrad(case):
+    """tc_wgrad.cu through b2no_pw_wgrad: dW, db vs float64, tensor-core and CUDA-core paths."""
+    from pde_policylearning_b200 import ops
+    B, co, ci, grid = case
+    dev = _dev()
+    torch.manual_seed(5)
+    g = torch.randn(B, co, *grid, device=dev)
+    x = torch.randn(B, ci, *grid, device=dev) + 0.5
+    dw64 = torch.einsum("bo...,bi...->oi", g.double(), x.double())
+    db64 = g.double().sum(dim=[0] + list(range(2, g.dim())))
+    try:
+        for mode in (True, False):
+            ops.set_tensor_core_mode(mode)
+            n0 = ops.tensor_core_launches()
+            dw, db = ops.pw_wgrad(g, x, need_bias=True)
+            assert (ops.tensor_core_launches() > n0) == mode
+            assert rel(dw, dw64) < TOL and rel(db, db64) < TOL, (mode, rel(dw, dw64), rel(db, db64))
+    finally:
+        ops.set_tensor_core_mode(True)
+
+
+@pytest.mark.parametrize("case", [(2, 32, 256, (128, 128), "gelu", False), (2, 34, 136, (32, 32), "relu", False),
+                                  (2, 64, 128, (16, 16, 8), "gelu", True), (1, 8, 16, (16, 8), "tanh", False)], ids=str)
+def test_tensor_core_mlp_head(case):
+    """tc_mlp.cu: fused Ci -> hidden -> act -> 1 head, forward and backward, vs float64 autograd."""
+    import pde_policylearning_b200 as P
+    from pde_policylearning_b200 import ops
+    B, ci, hid, grid, act, per_sample = case
+    dev = _dev()
+    torch.manual_seed(6)
+    nd = len(grid)
+    x = torch.randn(B, ci, *grid, device=dev, requires_grad=True)
+    w1 = (torch.randn(hid, ci, device=dev) * 0.3).requires_grad_(True)
+    b1 = torch.randn(*((B, hid) if per_sample else (hid,)), device=dev, requires_grad=True)
+    w2 = (torch.randn(1, hid, device=dev) * 0.3).requires_grad_(True)
+    b2 = torch.randn(1, device=dev, requires_grad=True)
+    gout = torch.randn(B, 1, *grid, device=dev)
+    f = {"gelu": torch.nn.functional.gelu, "relu": torch.relu, "tanh": torch.tanh}[act]
+    xd, w1d, b1d, w2d, b2d = (t.detach().double().requires_grad_(True) for t in (x, w1, b1, w2, b2))
+    bshape = (B, hid) + (1,) * nd if per_sample else (1, hid) + (1,) * nd
+    h = f(torch.einsum("ji,bi...->bj...", w1d, xd) + b1d.reshape(bshape))
+    ref = torch.einsum("oj,bj...->bo...", w2d, h) + b2d.reshape((1, 1) + (1,) * nd)
+    gref = torch.autograd.grad(ref, [xd, w1d, b1d, w2d, b2d], gout.double())
+    n0 = ops.tensor_core_launches()
+    out = P.mlp_head(x, w1, b1, w2, b2, act)
+    gs = torch.autograd.grad(out, [x, w1, b1, w2, b2], gout)
+    assert ops.tensor_core_launches() - n0 >= 3, "fused tensor-core head did not run"
+    assert rel(out, ref) < TOL
+    for name, a, b in zip(("dx", "dw1", "db1", "dw2", "db2"), gs, gref):
+        assert rel(a, b) < 2e-5, (name, rel(a, b))

@@ -125,3 +125,25 @@ def test_convert_shares_parameters_with_reference_modules():
         assert list(c.state_dict().keys()) == keys
         native = [m for m in c.modules() if type(m).__module__.startswith("pde_policylearning_b200")]
         assert native, "nothing was converted"
+
+
+def test_fast_erf_coefficients():
+    """The rational erf used by the CUDA GELU (csrc/common.cuh::b2no_erf), restated in numpy float32:
+    pins the coefficients and the accuracy claim without a GPU."""
+    import numpy as np
+    src = open(os.path.join(ROOT, "pde_policylearning_b200", "csrc", "common.cuh")).read()
+    body = src[src.index("float b2no_erf"):src.index("return __fdividef")]
+    nums = [float(t) for t in re.findall(r"-?\d\.\d+e-\d+", body)]
+    assert len(nums) == 12
+    a, b = nums[:7], nums[7:]
+    x = np.clip(np.linspace(-6, 6, 400001), -4, 4).astype(np.float32)
+    x2 = x * x
+    p = np.full_like(x, a[0])
+    for c in a[1:]:
+        p = p * x2 + np.float32(c)
+    q = np.full_like(x, b[0])
+    for c in b[1:]:
+        q = q * x2 + np.float32(c)
+    approx = (x * p / q).astype(np.float64)
+    ref = torch.erf(torch.linspace(-6, 6, 400001, dtype=torch.float64)).numpy()
+    assert np.abs(approx - ref).max() < 6e-7
