@@ -161,6 +161,14 @@ int b2no_rel_l2_sums(const float* x, const float* y, float* sums, int batch, int
 int b2no_rel_l2_bwd(const float* x, const float* y, const float* coef, float* dx, int batch,
                     int64_t n_per_sample, void* stream);
 
+/* ---- optimizer ---------------------------------------------------------------- */
+/* One fused Adam update over a flat fp32 buffer (complex parameters as their (re, im) view), torch.optim.Adam
+ * semantics as the reference configures it (run_pde_observers.py:134, train_pino.py:205): L2 weight decay,
+ * bias correction.  grad_scale multiplies the gradient first (1/world_size after a sum all-reduce).
+ * step_counter is a DEVICE int incremented by the call, so a captured CUDA graph replays correctly. */
+int b2no_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int* step_counter,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,7 +11,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2no.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["plan.cu", "spectral.cu", "pointwise.cu", "tc_pointwise.cu", "tc_wgrad.cu", "tc_mlp.cu"]
+SOURCES = ["plan.cu", "spectral.cu", "pointwise.cu", "tc_pointwise.cu", "tc_wgrad.cu", "tc_mlp.cu", "optim.cu"]
 
 MAX_DIM = 3
 NORM = {"backward": 0, "forward": 1, "ortho": 2}
@@ -98,10 +98,10 @@ def lib():
     L.b2no_rno_gate_bwd.argtypes = [vp] * 9 + [i64, vp]
     L.b2no_rel_l2_sums.argtypes = [vp, vp, vp, i32, i64, vp]
     L.b2no_rel_l2_bwd.argtypes = [vp, vp, vp, vp, i32, i64, vp]
+    f32 = C.c_float
+    L.b2no_adam_step.argtypes = [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, f32, vp]
     for name in EXPORTS:
-        fn = getattr(L, name)
-        if fn.restype is C.c_int and name not in ("b2no_version",):
-            pass
+        getattr(L, name)
     _lib = L
     return L
 
@@ -113,6 +113,7 @@ EXPORTS = [
     "b2no_dft_forward", "b2no_dft_inverse", "b2no_mix", "b2no_mix_dw",
     "b2no_act_bwd", "b2no_pw_wgrad_scratch_floats", "b2no_pw_wgrad", "b2no_mlp_head_fwd", "b2no_mlp_head_bwd_scratch_floats", "b2no_mlp_head_bwd_supported", "b2no_mlp_head_bwd",
     "b2no_rno_gate_fwd", "b2no_rno_gate_bwd", "b2no_rel_l2_sums", "b2no_rel_l2_bwd",
+    "b2no_adam_step",
 ]
 
 

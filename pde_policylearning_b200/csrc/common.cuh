@@ -75,6 +75,60 @@ __device__ __forceinline__ float b2no_erf(float x) {
   return __fdividef(x * p, q);
 }
 
+// ---- packed fp32x2 forms (FFMA2 / FMUL2 / FADD2, sm_100): one FMA-pipe instruction per TWO elements, no branches.
+// Same rational erf as above; the quotient uses MUFU.RCP (1 ulp), the Gaussian of the derivative MUFU.EX2.
+__device__ __forceinline__ float2 b2no_f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float b2no_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float b2no_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float2 b2no_erf2(float2 x) {
+  x.x = fminf(fmaxf(x.x, -4.0f), 4.0f);
+  x.y = fminf(fmaxf(x.y, -4.0f), 4.0f);
+  const float2 x2 = __fmul2_rn(x, x);
+  float2 p = b2no_f2(-2.72614225801306e-10f);
+  p = __ffma2_rn(p, x2, b2no_f2(2.77068142495902e-08f));
+  p = __ffma2_rn(p, x2, b2no_f2(-2.10102402082508e-06f));
+  p = __ffma2_rn(p, x2, b2no_f2(-5.69250639462346e-05f));
+  p = __ffma2_rn(p, x2, b2no_f2(-7.34990630326855e-04f));
+  p = __ffma2_rn(p, x2, b2no_f2(-2.95459980854025e-03f));
+  p = __ffma2_rn(p, x2, b2no_f2(-1.60960333262415e-02f));
+  float2 q = b2no_f2(-1.45660718464996e-05f);
+  q = __ffma2_rn(q, x2, b2no_f2(-2.13374055278905e-04f));
+  q = __ffma2_rn(q, x2, b2no_f2(-1.68282697438203e-03f));
+  q = __ffma2_rn(q, x2, b2no_f2(-7.37332916720468e-03f));
+  q = __ffma2_rn(q, x2, b2no_f2(-1.42647390514189e-02f));
+  const float2 r = make_float2(b2no_rcp(q.x), b2no_rcp(q.y));
+  return __fmul2_rn(__fmul2_rn(x, p), r);
+}
+// gelu(x) = 0.5 x (1 + erf(x / sqrt 2))
+__device__ __forceinline__ float2 b2no_gelu2(float2 x) {
+  const float2 e = b2no_erf2(__fmul2_rn(x, b2no_f2(0.70710678118654752440f)));
+  const float2 h = __fmul2_rn(x, b2no_f2(0.5f));
+  return __ffma2_rn(h, e, h);
+}
+// gelu(x) and gelu'(x) = Phi(x) + x phi(x) sharing the erf
+__device__ __forceinline__ void b2no_gelu2_both(float2 x, float2* val, float2* grad) {
+  const float2 e = b2no_erf2(__fmul2_rn(x, b2no_f2(0.70710678118654752440f)));
+  const float2 h = __fmul2_rn(x, b2no_f2(0.5f));
+  *val = __ffma2_rn(h, e, h);
+  const float2 cdf = __ffma2_rn(e, b2no_f2(0.5f), b2no_f2(0.5f));
+  const float2 t = __fmul2_rn(__fmul2_rn(x, x), b2no_f2(-0.72134752044448170368f));   // -0.5 x^2 log2(e)
+  const float2 g = make_float2(b2no_ex2(t.x), b2no_ex2(t.y));
+  *grad = __ffma2_rn(__fmul2_rn(x, b2no_f2(0.39894228040143267794f)), g, cdf);
+}
+__device__ __forceinline__ float2 b2no_gelu2_grad(float2 x) {
+  float2 v, g;
+  b2no_gelu2_both(x, &v, &g);
+  return g;
+}
+
 __device__ __forceinline__ float b2no_act(float x, int act) {
   switch (act) {
     case B2NO_ACT_GELU: return 0.5f * x * (1.0f + b2no_erf(x * 0.70710678118654752440f));

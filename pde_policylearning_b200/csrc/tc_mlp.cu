@@ -27,14 +27,14 @@ namespace {
 constexpr int kThreadsMlp = 448;
 
 struct MlpTc {
-  int B, Ci, Cip, H, Hp, NC, N2, Co2, S, fbufs, mode, act, b1_per_sample, dact;
+  int B, Ci, Cip, H, Hp, NC, N2, Co2, S, fbufs, mode, act, b1_per_sample, dact, direct;
   int tiles_per_img;
   long tiles, tiles_per_cta, P;
   const float* w1; const float* b1; const float* w2; const float* b2; const float* g; const float* dz;
   float* out; float* gz; float* dw2_partial;
 };
 
-struct MlpLayout { uint32_t w1h, w1l, w2h, w2l, b1, w2v, dw2, stages, stage_bytes, bars, total; };
+struct MlpLayout { uint32_t w1h, w1l, w2h, w2l, b1, w2v, dw2, part, stages, stage_bytes, bars, total; };
 
 __host__ __device__ inline MlpLayout mlp_layout(const MlpTc& p) {
   MlpLayout L;
@@ -45,26 +45,23 @@ __host__ __device__ inline MlpLayout mlp_layout(const MlpTc& p) {
   L.b1 = o; o += (uint32_t)p.Hp * 4;
   L.w2v = o; o += (uint32_t)p.Hp * 4;
   L.dw2 = o; o += (uint32_t)p.Hp * 4;
+  L.part = o; o += 2 * 128 * 4;
   o = (o + 1023u) & ~1023u;
   L.stages = o;
   L.stage_bytes = (uint32_t)p.Cip * 512;
   o += L.stage_bytes * p.S;
   L.bars = o;
-  o += 8 * (2 * p.S + 16) + 16;
+  o += 8 * (2 * p.S + 20) + 16;
   L.total = o + 1024;
   return L;
 }
 
 __host__ __device__ inline uint32_t mlp_tmem_cols(const MlpTc& p) {
+  if (p.direct) return 2u * p.Cip + 256u;
   return 2u * p.Cip + 128u + 128u * p.fbufs + 2u * p.N2;
 }
 
-template <bool GELU>
-__device__ __forceinline__ float act_f(float z, int act) { return GELU ? b2no_act(z, B2NO_ACT_GELU) : b2no_act(z, act); }
-template <bool GELU>
-__device__ __forceinline__ float act_g(float z, int act) { return GELU ? b2no_act_grad(z, B2NO_ACT_GELU) : b2no_act_grad(z, act); }
-
-template <bool GELU>
+template <bool GELU, bool BWD, bool DIRECT>
 __global__ void __launch_bounds__(kThreadsMlp, 1)
 k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
   extern __shared__ uint8_t smem_raw[];
@@ -75,8 +72,8 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
   uint64_t* x_full = empty + p.S;
   uint64_t* x_empty = x_full + 1;
   uint64_t* acc1_full = x_empty + 1;
-  uint64_t* acc1_empty = acc1_full + 2;
-  uint64_t* f_full = acc1_empty + 2;
+  uint64_t* acc1_empty = acc1_full + 4;
+  uint64_t* f_full = acc1_empty + 4;
   uint64_t* f_empty = f_full + 2;
   uint64_t* acc2_full = f_empty + 2;
   uint64_t* acc2_empty = acc2_full + 2;
@@ -84,7 +81,10 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint32_t ncols = 32;
   while (ncols < mlp_tmem_cols(p)) ncols <<= 1;
-  const bool bwd = p.mode == 1;
+  constexpr bool bwd = BWD;
+  // DIRECT (forward, one output channel): out = b2 + sum_j w2[j] act(z1[j]) is accumulated by the epilogue threads in fp32
+  // registers (FFMA2) -- no F operand, no second MMA; exact fp32 accumulation for the cancelling sum over the hidden units
+  constexpr bool direct = DIRECT;
 
   // ---- setup: W1 (B operand of MMA1, [Hp x Cip]) and W2' (B operand of MMA2, [N2 x Hp]), hi/lo, K-major core layout ----
   for (int i = tid; i < p.Hp * p.Cip; i += kThreadsMlp) {
@@ -107,14 +107,14 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
   }
   for (int i = tid; i < p.Hp; i += kThreadsMlp) {
     ((float*)(smem + L.b1))[i] = (!p.b1_per_sample && p.b1 && i < p.H) ? p.b1[i] : 0.f;
-    ((float*)(smem + L.w2v))[i] = (bwd && i < p.H) ? p.w2[i] : 0.f;
+    ((float*)(smem + L.w2v))[i] = ((bwd || direct) && i < p.H) ? p.w2[i] : 0.f;
     ((float*)(smem + L.dw2))[i] = 0.f;
   }
   if (tid == 0) {
     for (int s = 0; s < p.S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 128); }
     mbar_init(x_full, 128); mbar_init(x_empty, 1);
+    for (int a = 0; a < 4; a++) { mbar_init(&acc1_full[a], 1); mbar_init(&acc1_empty[a], 256); }
     for (int a = 0; a < 2; a++) {
-      mbar_init(&acc1_full[a], 1); mbar_init(&acc1_empty[a], 256);
       mbar_init(&f_full[a], 256); mbar_init(&f_empty[a], 1);
       mbar_init(&acc2_full[a], 1); mbar_init(&acc2_empty[a], 256);
     }
@@ -128,7 +128,8 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
   tc_fence_after();
   const uint32_t tbase = *tslot;
   // TMEM map: [X hi | X lo] [acc1 x2] [F (hi 64 | lo 64) x fbufs] [acc2 x2]
-  const uint32_t t_x = tbase, t_acc1 = t_x + 2u * p.Cip, t_f = t_acc1 + 128u, t_acc2 = t_f + 128u * p.fbufs;
+  constexpr int NA = DIRECT ? 4 : 2;   // acc1 ring depth (DIRECT has no F / acc2, so the TMEM goes to a deeper ring)
+  const uint32_t t_x = tbase, t_acc1 = t_x + 2u * p.Cip, t_f = t_acc1 + 64u * NA, t_acc2 = t_f + 128u * p.fbufs;
   const long t_first = (long)blockIdx.x * p.tiles_per_cta;
   const long t_end = t_first + p.tiles_per_cta < p.tiles ? t_first + p.tiles_per_cta : p.tiles;
   const int NC = p.NC;
@@ -157,8 +158,8 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
     int it = 0;
     long n1 = 0;  // chunk counter of this CTA (acc1 / F ring position)
     auto mma1 = [&](long n, int c) {
-      const int ab = (int)(n & 1);
-      mbar_wait(&acc1_empty[ab], ((uint32_t)(n >> 1) & 1u) ^ 1u);
+      const int ab = (int)(n % NA);
+      mbar_wait(&acc1_empty[ab], ((uint32_t)(n / NA) & 1u) ^ 1u);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t d = t_acc1 + 64u * ab;
@@ -176,6 +177,13 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
     for (long tile = t_first; tile < t_end; tile++, it++) {
       mbar_wait(x_full, (uint32_t)it & 1u);
       tc_fence_after();
+      if (direct) {
+        for (int c = 0; c < NC; c++) mma1(n1 + c, c);
+        if (elect_one()) mma_commit(x_empty);
+        __syncwarp();
+        n1 += NC;
+        continue;
+      }
       mma1(n1, 0);
       if (NC > 1) mma1(n1 + 1, 1);
       if (NC <= 2) { if (elect_one()) mma_commit(x_empty); __syncwarp(); }
@@ -250,31 +258,69 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
       const long px = (tile - (long)b * p.tiles_per_img) * 128 + t;
       const float gv = bwd ? __ldg(p.g + (size_t)b * p.P + px) : 0.f;
       const float* b1g = p.b1_per_sample ? p.b1 + (size_t)b * p.H : nullptr;
+      float2 oacc = make_float2(0.f, 0.f);
       for (int c = 0; c < NC; c++) {
         const long n = n1 + c;
-        const int ab = (int)(n & 1);
+        const int ab = (int)(n % NA);
         const int col0 = c * 64 + half * 32;   // first hidden index of this thread's 32 columns
-        mbar_wait(&acc1_full[ab], (uint32_t)(n >> 1) & 1u);
+        mbar_wait(&acc1_full[ab], (uint32_t)(n / NA) & 1u);
         tc_fence_after();
         float v[32];
-        tmem_ld16(t_acc1 + lane_base + 64u * ab + half * 32, v);
-        tmem_ld16(t_acc1 + lane_base + 64u * ab + half * 32 + 16, v + 16);
+        tmem_ld32(t_acc1 + lane_base + 64u * ab + half * 32, v);
+        // hidden bias for this thread's 32 columns (loads overlap the TMEM read); pad columns (>= H) carry zero
+        // W1 rows, zero w2 and a finite bias, so they contribute exactly 0 and need no branches
+        float bj[32];
+        if (b1g) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) bj[j] = __ldg(b1g + min(col0 + j, p.H - 1));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(bj + j) = *reinterpret_cast<const float4*>(sb1 + col0 + j);
+        }
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&acc1_empty[ab]);
         float ga[32];
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-          const int hj = col0 + j;
-          const float bj = b1g ? (hj < p.H ? __ldg(b1g + hj) : 0.f) : sb1[hj];
-          const float z = v[j] + bj;
+        if (GELU) {
+          // packed fp32x2 math: one FMA-pipe instruction per two hidden units
+          float2* v2 = reinterpret_cast<float2*>(v);
+          const float2* b2 = reinterpret_cast<const float2*>(bj);
           if (bwd) {
-            ga[j] = gv * act_f<GELU>(z, p.act);
-            v[j] = gv * sw2[hj] * act_g<GELU>(z, p.act);
+            float2* ga2 = reinterpret_cast<float2*>(ga);
+            const float2 gv2 = b2no_f2(gv);
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              const float2 w2p = *reinterpret_cast<const float2*>(sw2 + col0 + 2 * j);
+              float2 val, grad;
+              b2no_gelu2_both(__fadd2_rn(v2[j], b2[j]), &val, &grad);
+              ga2[j] = __fmul2_rn(gv2, val);
+              v2[j] = __fmul2_rn(__fmul2_rn(gv2, w2p), grad);
+            }
+          } else if (direct) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              const float2 w2p = *reinterpret_cast<const float2*>(sw2 + col0 + 2 * j);
+              oacc = __ffma2_rn(b2no_gelu2(__fadd2_rn(v2[j], b2[j])), w2p, oacc);
+            }
           } else {
-            v[j] = act_f<GELU>(z, p.act);
+#pragma unroll
+            for (int j = 0; j < 16; j++) v2[j] = b2no_gelu2(__fadd2_rn(v2[j], b2[j]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const float z = v[j] + bj[j];
+            if (bwd) {
+              ga[j] = gv * b2no_act(z, p.act);
+              v[j] = gv * sw2[col0 + j] * b2no_act_grad(z, p.act);
+            } else if (direct) {
+              oacc.x = fmaf(b2no_act(z, p.act), sw2[col0 + j], oacc.x);
+            } else {
+              v[j] = b2no_act(z, p.act);
+            }
           }
         }
+        if (direct) continue;
         if (bwd) {
           if (p.gz) {
             float* gp = p.gz + ((size_t)b * p.H + col0) * p.P + px;
@@ -315,6 +361,15 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
         mbar_arrive(&f_full[fb]);
       }
       n1 += NC;
+      if (direct) {
+        // the two column halves of a pixel live in different warps: combine through shared memory (double buffered,
+        // one named barrier over the 256 epilogue threads per tile)
+        float* part = (float*)(smem + L.part) + (it & 1) * 128;
+        if (half == 1) part[t] = oacc.x + oacc.y;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0) p.out[(size_t)b * p.P + px] = (oacc.x + oacc.y) + part[t] + (p.b2 ? __ldg(p.b2) : 0.f);
+        continue;
+      }
       // ---- epilogue-2 ----
       const int a2 = it & 1;
       mbar_wait(&acc2_full[a2], (uint32_t)(it >> 1) & 1u);
@@ -368,6 +423,7 @@ int mlp_launch(MlpTc& p, const float* x, int batch, long pixels, cudaStream_t st
   p.P = pixels;
   p.tiles_per_img = (int)(pixels / 128);
   p.tiles = (long)batch * p.tiles_per_img;
+  p.direct = (p.mode == 0 && p.Co2 == 1) ? 1 : 0;
   p.fbufs = 2;
   if (mlp_tmem_cols(p) > 512) p.fbufs = 1;
   if (mlp_tmem_cols(p) > 512) return 1;
@@ -388,13 +444,16 @@ int mlp_launch(MlpTc& p, const float* x, int batch, long pixels, cudaStream_t st
   uint64_t str[3] = {4, (uint64_t)pixels * 4, (uint64_t)pixels * 4 * p.Ci};
   uint32_t box[3] = {128, (uint32_t)p.Cip, 1};
   if (make_tmap_f32(&tmx, x, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
-  if (p.act == B2NO_ACT_GELU) {
-    B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_mlp_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    k_mlp_tc<true><<<(unsigned)grid, kThreadsMlp, L.total, st>>>(tmx, p);
-  } else {
-    B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_mlp_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    k_mlp_tc<false><<<(unsigned)grid, kThreadsMlp, L.total, st>>>(tmx, p);
-  }
+#define MLP_LAUNCH(G, W, D)                                                                                              \
+  do {                                                                                                                   \
+    B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_mlp_tc<G, W, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total)); \
+    k_mlp_tc<G, W, D><<<(unsigned)grid, kThreadsMlp, L.total, st>>>(tmx, p);                                            \
+  } while (0)
+  const bool gelu = p.act == B2NO_ACT_GELU;
+  if (p.mode == 1) { if (gelu) MLP_LAUNCH(true, true, false); else MLP_LAUNCH(false, true, false); }
+  else if (p.direct) { if (gelu) MLP_LAUNCH(true, false, true); else MLP_LAUNCH(false, false, true); }
+  else { if (gelu) MLP_LAUNCH(true, false, false); else MLP_LAUNCH(false, false, false); }
+#undef MLP_LAUNCH
   B2NO_LAUNCH_CHECK();
   *grid_out = (int)grid;
   return 0;

@@ -1,0 +1,124 @@
+"""Fused flat-buffer Adam and the CUDA-graph training step.
+
+The reference trains with ``torch.optim.Adam(model.parameters(), lr, weight_decay)`` (run_pde_observers.py:134,
+train_pino.py:205): ~30 tiny foreach kernels per step for a 600 k-parameter FNO2d.  Here every parameter, gradient
+and moment lives in ONE flat fp32 buffer (complex parameters as their real view, which is how torch.optim.Adam
+treats them), the update is one kernel (csrc/optim.cu), and the 1/world_size of the data-parallel mean is folded
+into it.  ``GraphedTrainStep`` captures forward + loss + backward + all-reduce + Adam into one CUDA graph."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from .parallel import GradBucket
+
+
+class FusedAdam:
+    """Adam with torch.optim.Adam's update rule over a flat parameter buffer.
+
+    After construction every ``p.data`` is a view into ``self.flat_param`` and every ``p.grad`` a view into
+    ``self.bucket.flat`` (so ``state_dict()`` / checkpoints of the MODEL are unchanged)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                 bucket: Optional[GradBucket] = None):
+        self.bucket = bucket if bucket is not None else GradBucket(params)
+        ps = self.bucket.params
+        if not ps:
+            raise ValueError("FusedAdam got no trainable parameters")
+        dev = ps[0].device
+        ops._require_cuda(*ps)
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+        n = self.bucket.numel
+        self.flat_param = torch.zeros(n, dtype=torch.float32, device=dev)
+        for p, off in zip(ps, self.bucket.offsets):
+            k = (2 if p.is_complex() else 1) * p.numel()
+            chunk = self.flat_param[off: off + k]
+            view = torch.view_as_complex(chunk.view(*p.shape, 2)) if p.is_complex() else chunk.view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+        if self.bucket.flat is None:
+            self.bucket.attach()
+        self.exp_avg = torch.zeros_like(self.flat_param)
+        self.exp_avg_sq = torch.zeros_like(self.flat_param)
+        self.step_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.bucket.zero()
+
+    def step(self, grad_scale: float = 1.0):
+        L = _lib.lib()
+        _lib.check(L.b2no_adam_step(ops._ptr(self.flat_param), ops._ptr(self.bucket.flat), ops._ptr(self.exp_avg),
+                                    ops._ptr(self.exp_avg_sq), self.bucket.numel, ops._ptr(self.step_counter),
+                                    self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                    float(grad_scale), ops._stream()), "adam_step")
+        ops.LAUNCHES[0] += 2
+
+    def state_dict(self):
+        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_counter,
+                "lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay}
+
+    def load_state_dict(self, sd):
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.step_counter.copy_(sd["step"])
+        self.lr, self.betas, self.eps, self.weight_decay = sd["lr"], tuple(sd["betas"]), sd["eps"], sd["weight_decay"]
+
+
+class GraphedTrainStep:
+    """One training step -- zero grads, forward, loss, backward, (sum all-reduce), fused Adam -- captured ONCE
+    into a CUDA graph and replayed: the ~150 launches of a step cost one cudaGraphLaunch on the host.
+
+        step = GraphedTrainStep(model, loss_fn, opt, example_inputs, example_target)
+        loss = step(inputs, target)          # copies into the static buffers, replays, returns the loss tensor
+
+    ``loss_fn(output, target)``; inputs is a tuple of tensors (device or pinned host: the copy into the static
+    input buffers is the H2D transfer)."""
+
+    def __init__(self, model, loss_fn: Callable, opt: FusedAdam, example_inputs, example_target, warmup: int = 3,
+                 group=None):
+        self.model, self.loss_fn, self.opt, self.group = model, loss_fn, opt, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        dev = opt.flat_param.device
+        self.static_in = [torch.empty_like(t, device=dev).copy_(t) for t in example_inputs]
+        self.static_tgt = torch.empty_like(example_target, device=dev).copy_(example_target)
+        # warm-up on a side stream (plans, tensor maps, allocator pools), then restore the optimizer state so that
+        # construction does not advance training
+        saved = (opt.flat_param.clone(), opt.exp_avg.clone(), opt.exp_avg_sq.clone(), opt.step_counter.clone())
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._eager()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = ops.LAUNCHES[0]
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._eager()
+        self.launches_per_step = ops.LAUNCHES[0] - l0
+        for dst, src in zip((opt.flat_param, opt.exp_avg, opt.exp_avg_sq, opt.step_counter), saved):
+            dst.copy_(src)
+
+    def _eager(self):
+        self.opt.zero_grad()
+        out = self.model(*self.static_in)
+        loss = self.loss_fn(out, self.static_tgt)
+        loss.backward()
+        if self.world > 1:
+            dist.all_reduce(self.opt.bucket.flat, op=dist.ReduceOp.SUM, group=self.group)
+        self.opt.step(grad_scale=1.0 / self.world)
+        return loss.detach()
+
+    def __call__(self, inputs, target):
+        for dst, src in zip(self.static_in, inputs):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        if self.static_tgt.data_ptr() != target.data_ptr():
+            self.static_tgt.copy_(target, non_blocking=True)
+        self.graph.replay()
+        ops.LAUNCHES[0] += self.launches_per_step
+        return self.static_loss

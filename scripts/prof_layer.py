@@ -23,10 +23,31 @@ for _ in range(iters):
         y = ops.dft_inverse(plan, 0, yh, ops.make_epilogue(bias=bias, pw_w=w, pw_x=x, preact=z, act="gelu"))
     if what in ("all", "wgrad"):
         ops.pw_wgrad(z, x, need_bias=False)
+if what in ("all", "mlp"):
+    import pde_policylearning_b200 as P
+    w1 = (torch.randn(256, C, device=dev) * 0.2).requires_grad_(True)
+    b1 = torch.randn(256, device=dev, requires_grad=True)
+    w2 = (torch.randn(1, 256, device=dev) * 0.2).requires_grad_(True)
+    b2 = torch.randn(1, device=dev, requires_grad=True)
+    xr = x.clone().requires_grad_(True)
+    for _ in range(iters):
+        out = P.mlp_head(xr, w1, b1, w2, b2, "gelu")
+        out.backward(torch.ones_like(out))
 torch.cuda.synchronize()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 if what == "time":
-    for name, fn in (("fwd", lambda: ops.dft_forward(plan, 0, x)),
+    import pde_policylearning_b200 as P
+    w1 = (torch.randn(256, C, device=dev) * 0.2).requires_grad_(True)
+    b1 = torch.randn(256, device=dev, requires_grad=True)
+    w2 = (torch.randn(1, 256, device=dev) * 0.2).requires_grad_(True)
+    b2 = torch.randn(1, device=dev, requires_grad=True)
+    xr = x.clone().requires_grad_(True)
+    gout = torch.ones(B, 1, N, N, device=dev)
+    w1m, w2v = w1.detach(), w2.detach().reshape(-1)
+    for name, fn in (("mlp_fwd", lambda: ops.mlp_head_fwd(x, w1m, b1.detach(), w2v, b2.detach(), "gelu")),
+                     ("mlp_bwd", lambda: ops.mlp_head_bwd(x, w1m, b1.detach(), w2v, gout, "gelu", want_gz=True)),
+                     ("mlp_bwd_nogz", lambda: ops.mlp_head_bwd(x, w1m, b1.detach(), w2v, gout, "gelu", want_gz=False)),
+("fwd", lambda: ops.dft_forward(plan, 0, x)),
                      ("inv", lambda: ops.dft_inverse(plan, 0, yh, ops.make_epilogue(bias=bias, pw_w=w, pw_x=x))),
                      ("invgelu", lambda: ops.dft_inverse(plan, 0, yh, ops.make_epilogue(bias=bias, pw_w=w, pw_x=x, preact=z, act="gelu"))),
                      ("wgrad", lambda: ops.pw_wgrad(z, x, need_bias=False))):

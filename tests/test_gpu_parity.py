@@ -496,3 +496,62 @@ def test_tensor_core_mlp_head(case):
     assert rel(out, ref) < TOL
     for name, a, b in zip(("dx", "dw1", "db1", "dw2", "db2"), gs, gref):
         assert rel(a, b) < 2e-5, (name, rel(a, b))
+
+
+# --------------------------------------------------------------------------------------------
+# fused Adam (csrc/optim.cu) and the CUDA-graph training step
+# --------------------------------------------------------------------------------------------
+def test_fused_adam_matches_torch_adam():
+    """Same update rule as torch.optim.Adam(lr, weight_decay) incl. complex parameters (run_pde_observers.py:134)."""
+    import pde_policylearning_b200 as P
+    dev = _dev()
+    torch.manual_seed(21)
+    shapes = [((7, 5), False), ((3,), False), ((4, 3, 2, 2), True), ((1,), False), ((130,), False)]
+    mk = lambda: [torch.nn.Parameter(torch.randn(*s, dtype=torch.cfloat if c else torch.float32, device=dev)) for s, c in shapes]
+    torch.manual_seed(22)
+    pa = mk()
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    ref = torch.optim.Adam(pb, lr=3e-3, weight_decay=1e-4)
+    opt = P.FusedAdam(pa, lr=3e-3, weight_decay=1e-4)
+    for it in range(5):
+        opt.zero_grad()
+        ref.zero_grad()
+        for a, b in zip(pa, pb):
+            g = torch.randn_like(a)
+            a.grad.copy_(g)
+            b.grad = g.clone()
+        opt.step()
+        ref.step()
+    for a, b in zip(pa, pb):
+        assert rel(a.detach(), b.detach()) < 1e-6
+
+
+def test_graphed_train_step_matches_eager():
+    """GraphedTrainStep (one CUDA graph per step) follows the same trajectory as the eager step."""
+    import pde_policylearning_b200 as P
+    dev = _dev()
+
+    def build():
+        torch.manual_seed(31)
+        m = P.FNO2dObserver(6, 6, 8).to(dev)
+        return m, P.FusedAdam(m.parameters(), lr=1e-3, weight_decay=1e-4)
+
+    torch.manual_seed(32)
+    xs = [torch.randn(4, 16, 16, 1, device=dev) for _ in range(3)]
+    ts = [torch.randn(4, 1, 16, 16, device=dev) for _ in range(3)]
+    loss_fn = lambda o, t: P.rel_l2_loss(o, t, size_average=False)
+    m1, o1 = build()
+    eager = []
+    for x, t in zip(xs, ts):
+        o1.zero_grad()
+        loss = loss_fn(m1(x), t)
+        loss.backward()
+        o1.step()
+        eager.append(loss.item())
+    m2, o2 = build()
+    step = P.GraphedTrainStep(m2, loss_fn, o2, (xs[0],), ts[0])
+    graphed = [step((x,), t).item() for x, t in zip(xs, ts)]
+    for a, b in zip(eager, graphed):
+        assert abs(a - b) < 1e-5 * abs(a), (eager, graphed)
+    assert rel(o2.flat_param, o1.flat_param) < 1e-5
+    assert int(o2.step_counter.item()) == 3
