@@ -172,55 +172,77 @@ def _time_op(fn, iters=10, warm=3):
     return sum(ts) / len(ts) * 1e-3  # seconds, mean
 
 
-def kernel_probes(dev, hbm_peak_gbs):
-    """Times the streaming kernels of one Fourier layer at the workload's shape, each alone, back to back
-    over DIFFERENT buffers (working set 4 x 134 MB > L2)."""
+def kernel_probes(dev, hbm_peak_gbs, tf32_peak_tflops):
+    """Times every hot kernel group of one training step at the workload's shape, each alone, with CUDA events on
+    the launching stream, rotating over 3 buffer sets (working set > 126 MB L2).  Algorithmic bytes / flops per
+    launch are SURVEY.md 8d's formulas."""
     from pde_policylearning_b200 import ops
-    B, C, N = BATCH, WIDTH, GRID
+    B, C, N, H = BATCH, WIDTH, GRID, 256
     geom = ops.SpecGeom(nin=(N, N), half=(MODES // 2, MODES // 2), norm="forward")
     plan = ops.get_plan(geom, dev)
     nbuf = 3
     xs = [torch.randn(B, C, N, N, device=dev) for _ in range(nbuf)]
+    outs = [torch.empty(B, C, N, N, device=dev) for _ in range(nbuf)]
+    zs = [torch.empty(B, C, N, N, device=dev) for _ in range(nbuf)]
+    spec = [torch.randn(B, C, *plan.kept, dtype=torch.complex64, device=dev) for _ in range(nbuf)]
     w = torch.randn(C, C, device=dev)
     bias = torch.randn(C, device=dev)
-    spec = [torch.randn(B, C, *plan.kept, dtype=torch.complex64, device=dev) for _ in range(nbuf)]
+    w1, b1 = torch.randn(H, C, device=dev) * 0.2, torch.randn(H, device=dev)
+    w2, b2 = torch.randn(H, device=dev) * 0.2, torch.randn(1, device=dev)
+    g1 = [torch.randn(B, 1, N, N, device=dev) for _ in range(nbuf)]
     state = {"i": 0}
-    L = ops._lib.lib()
-    import ctypes as Cc
-    work = plan.workspace(B, C)
-    outs = [torch.empty(B, C, N, N, device=dev) for _ in range(nbuf)]
-    A = torch.empty(B * C * N, plan.kept[1], dtype=torch.complex64, device=dev)
-    st = Cc.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def nxt():
+        state["i"] = (state["i"] + 1) % nbuf
+        return state["i"]
 
     def fwd_dft():
-        i = state["i"] = (state["i"] + 1) % nbuf
-        ops.check(L.b2no_dft_forward(plan.handle, 0, ops._ptr(xs[i]), ops._ptr(spec[i]), ops._ptr(work), B * C, st))
+        ops.dft_forward(plan, 0, xs[nxt()])
 
     def inv_fused():
-        i = state["i"] = (state["i"] + 1) % nbuf
-        epi = ops.make_epilogue(bias=bias, pw_w=w, pw_x=xs[i], act="gelu")
-        ops.check(L.b2no_dft_inverse(plan.handle, 0, ops._ptr(spec[i]), ops._ptr(outs[i]), ops._ptr(work), B, C,
-                                     N * N, Cc.byref(epi), st))
+        i = nxt()
+        ops.dft_inverse(plan, 0, spec[i], ops.make_epilogue(bias=bias, pw_w=w, pw_x=xs[i]), out=outs[i])
+
+    def inv_fused_gelu():
+        i = nxt()
+        ops.dft_inverse(plan, 0, spec[i], ops.make_epilogue(bias=bias, pw_w=w, pw_x=xs[i], preact=zs[i], act="gelu"), out=outs[i])
 
     def wgrad():
-        i = state["i"] = (state["i"] + 1) % nbuf
+        i = nxt()
         ops.pw_wgrad(xs[i], outs[(i + 1) % nbuf], need_bias=False)
 
-    bytes_x = B * C * N * N * 4
+    def head_fwd():
+        ops.mlp_head_fwd(xs[nxt()], w1, b1, w2, b2, "gelu")
+
+    def head_bwd():
+        i = nxt()
+        ops.mlp_head_bwd(xs[i], w1, b1, w2, g1[i], "gelu", want_gz=True)
+
+    bx = B * C * N * N * 4
     K = plan.modes
-    probes = []
-    # algorithmic bytes (SURVEY 8d): forward DFT reads x once, writes the kept spectrum
-    t = _time_op(fwd_dft)
-    probes.append(dict(kernel="dft_forward (k_r2c_last + k_cmat)", seconds=t, bytes=bytes_x + B * C * K * 8,
-                       launches_per_step=8))
-    t = _time_op(inv_fused)
-    probes.append(dict(kernel="dft_inverse fused (k_cmat + k_c2r_fused: irfft + bias + 1x1 skip + GELU)", seconds=t,
-                       bytes=2 * bytes_x + B * C * K * 8, launches_per_step=8))
-    t = _time_op(wgrad)
-    probes.append(dict(kernel="pw_wgrad (1x1 skip weight gradient)", seconds=t, bytes=2 * bytes_x, launches_per_step=4))
+    px = B * N * N
+    probes = [
+        dict(kernel="dft_forward (k_r2c_last + k_cmat)", fn=fwd_dft, bound="hbm", bytes=bx + B * C * K * 8, n=8),
+        dict(kernel="dft_inverse + bias + 1x1 skip (k_inv_h + k_pw_tc<1>)", fn=inv_fused, bound="hbm", bytes=2 * bx + B * C * K * 8, n=6),
+        dict(kernel="dft_inverse + bias + 1x1 skip + GELU, z saved (k_inv_h + k_pw_tc<2>)", fn=inv_fused_gelu, bound="hbm",
+             bytes=3 * bx + B * C * K * 8, n=2),
+        dict(kernel="1x1 weight gradient (k_wgrad_tc + reduce)", fn=wgrad, bound="hbm", bytes=2 * bx, n=4),
+        dict(kernel="projection head forward (k_mlp_tc<fwd>)", fn=head_fwd, bound="tensor", bytes=bx + px * 4,
+             flops=2.0 * px * (C * H + H), n=1),
+        dict(kernel="projection head backward (k_mlp_tc<bwd>, gz written)", fn=head_bwd, bound="tensor",
+             bytes=2 * bx + px * 4 + px * H * 4, flops=2.0 * px * (2 * C * H + H), n=1),
+    ]
     for p in probes:
-        p["gbs"] = p["bytes"] / p["seconds"] / 1e9
-        p["frac"] = p["gbs"] / hbm_peak_gbs
+        t = _time_op(p.pop("fn"))
+        p["seconds"] = t
+        p["launches_per_step"] = p.pop("n")
+        p["gbs"] = p["bytes"] / t / 1e9
+        if p["bound"] == "tensor":
+            # fp32-accurate tensor-core mode issues every product three times (3xTF32): effective peak = TF32 / 3
+            p["tflops"] = p["flops"] / t / 1e12
+            p["frac"] = max(p["tflops"] * 3.0 / tf32_peak_tflops, p["gbs"] / hbm_peak_gbs)
+        else:
+            p["frac"] = p["gbs"] / hbm_peak_gbs
     return probes
 
 
@@ -237,22 +259,34 @@ def run_b200(args):
     torch.cuda.set_device(dev)
     torch.manual_seed(0)                                    # identical weights on every rank
     model = P.FNO2dObserver(MODES, MODES, WIDTH).to(dev)
-    loss_fn = P.LpLoss(size_average=False)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
-    bucket = parallel.GradBucket(model.parameters())
-    bucket.attach()
+    lp = P.LpLoss(size_average=False)
+    loss_fn = lambda out, tgt: lp(out, tgt)
+    opt = P.FusedAdam(model.parameters(), lr=1e-3, weight_decay=1e-4)   # run_pde_observers.py:134
     p_host = synthetic_fields(BATCH, GRID, seed=100 + rank).pin_memory()
     t_host = synthetic_fields(BATCH, GRID, seed=200 + rank).permute(0, 3, 1, 2).contiguous().pin_memory()
     p_dev, t_dev = p_host.to(dev), t_host.to(dev)
 
-    def step(p, t):
-        bucket.zero()
+    # one training step = zero grads, forward, rel-L2 loss, backward, (N>1: NCCL sum all-reduce of the flat gradient
+    # bucket), fused Adam -- captured once into a CUDA graph (P.GraphedTrainStep); --no-graph runs the same step eagerly
+    graphed = None
+    if not args.no_graph:
+        try:
+            graphed = P.GraphedTrainStep(model, loss_fn, opt, (p_dev,), t_dev, warmup=3)
+        except Exception as e:  # noqa: BLE001
+            print(f"warning: CUDA-graph capture failed ({type(e).__name__}: {e}); running the eager step", file=sys.stderr)
+            graphed = None
+
+    def eager_step(p, t):
+        opt.zero_grad()
         loss = loss_fn(model(p, None), t)
         loss.backward()
         if world > 1:
-            bucket.allreduce_mean()
-        opt.step()
-        return loss
+            dist.all_reduce(opt.bucket.flat, op=dist.ReduceOp.SUM)
+        opt.step(grad_scale=1.0 / world)
+        return loss.detach()
+
+    def step(p, t):
+        return graphed((p,), t) if graphed is not None else eager_step(p, t)
 
     def barrier():
         if world > 1:
@@ -272,26 +306,28 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    # resident inputs: the graph's static buffers already hold this rank's batch -> no copies in the timed region
+    res_in = (graphed.static_in[0], graphed.static_tgt) if graphed is not None else (p_dev, t_dev)
     for _ in range(args.warmup):
-        step(p_dev, t_dev)
+        step(*res_in)
     l0 = ops.LAUNCHES[0]
     with ClockSampler(local_rank) as clk:
-        ms = timed(lambda: step(p_dev, t_dev), args.steps)
+        ms = timed(lambda: step(*res_in), args.steps)
     launches = (ops.LAUNCHES[0] - l0) // args.steps
     clocks = clk.summary()
     ms_per_step = ms / args.steps
     value = BATCH * world / (ms_per_step * 1e-3)
 
-    # ---- e2e: pinned host inputs -> H2D -> public API -> loss.item() each step ----
+    # ---- e2e: pinned host inputs -> H2D -> public API step -> loss.item() (D2H) every step ----
     def e2e_step():
-        p = p_host.to(dev, non_blocking=True)
-        t = t_host.to(dev, non_blocking=True)
-        return step(p, t).item()
+        if graphed is not None:
+            return graphed((p_host,), t_host).item()
+        return eager_step(p_host.to(dev, non_blocking=True), t_host.to(dev, non_blocking=True)).item()
 
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps) / args.steps
-    e2e = {"value": BATCH * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+    e2e = {"value": round(BATCH * world / (ms_e2e * 1e-3), 2), "unit": UNIT, "ms_per_step": round(ms_e2e, 4),
            "h2d_bytes_per_step": p_host.numel() * 4 + t_host.numel() * 4, "d2h_bytes_per_step": 4}
 
     out = None
@@ -302,8 +338,11 @@ def run_b200(args):
         except Exception:
             pass
         hbm = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        probes = kernel_probes(dev, hbm)
+        bf16 = float(peaks.get("bf16_tflops", 1590.0))
+        tf32 = bf16 / 2.0
+        peak_src = ("measured (MEASURED_PEAKS.json: hbm_gbs; TF32 peak taken as bf16_tflops burst / 2, the datasheet ratio)"
+                    if "hbm_gbs" in peaks else "fallback 6650 GB/s, 1590 TFLOP/s bf16 / 2")
+        probes = kernel_probes(dev, hbm, tf32)
         for p in probes:
             p["share_of_step"] = p["seconds"] * p["launches_per_step"] / (ms_per_step * 1e-3)
         top = max(probes, key=lambda p: p["share_of_step"])
@@ -312,17 +351,25 @@ def run_b200(args):
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top["kernel"])
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": round(top["gbs"], 1), "peak": hbm,
-                    "unit": "GB/s", "frac": round(top["frac"], 4), "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": top["bytes"], "avg_launch_us": round(top["seconds"] * 1e6, 2),
-                    "all": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in p.items()} for p in probes]}
-        cpu = None
-        if world == 1 or True:
-            cpu = cpu_reference_run(steps=3, warmup=1, sample_batch=4)
+        if top["bound"] == "tensor":
+            roofline = {"bound": "tensor", "kernel": top["kernel"], "achieved": round(top["tflops"] * 3.0, 2), "peak": tf32,
+                        "unit": "TFLOP/s", "frac": round(top["frac"], 4), "traffic": traffic,
+                        "note": "achieved = algorithmic flops x 3 (3xTF32 issues each product three times) / launch time",
+                        "algorithmic_flops_per_launch": top["flops"]}
+        else:
+            roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": round(top["gbs"], 1), "peak": hbm,
+                        "unit": "GB/s", "frac": round(top["frac"], 4), "traffic": traffic}
+        roofline.update({"peak_source": peak_src, "algorithmic_bytes_per_launch": top["bytes"],
+                         "avg_launch_us": round(top["seconds"] * 1e6, 2),
+                         "all": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in p.items()} for p in probes]})
+        cpu = cpu_reference_run(steps=3, warmup=1, sample_batch=4)
+        cfg = config_dict(world)
+        cfg["cuda_graph"] = graphed is not None
+        cfg["optimizer"] = "fused flat Adam (lr 1e-3, weight_decay 1e-4), inside the timed step"
         out = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": config_dict(world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+               "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                "roofline": roofline, "cpu_baseline": cpu}
     if world > 1:
         dist.barrier()
@@ -353,6 +400,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="run the training step eagerly instead of as one CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

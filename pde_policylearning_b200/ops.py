@@ -202,7 +202,8 @@ def make_epilogue(bias=None, pw_w=None, pw_x=None, pw_transposed=False, pw2_w=No
     return e
 
 
-def dft_inverse(plan: Plan, which: int, spec: torch.Tensor, epi: Optional[Epilogue] = None) -> torch.Tensor:
+def dft_inverse(plan: Plan, which: int, spec: torch.Tensor, epi: Optional[Epilogue] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """spectrum (B, C, *kept) complex64 -> y (B, C, *grid) fp32, with the fused epilogue."""
     _require_cuda(spec)
     assert spec.dtype == torch.complex64 and spec.is_contiguous()
@@ -210,7 +211,7 @@ def dft_inverse(plan: Plan, which: int, spec: torch.Tensor, epi: Optional[Epilog
     if tuple(spec.shape[2:]) != plan.kept:
         raise ValueError(f"expected kept modes {plan.kept}, got {tuple(spec.shape[2:])}")
     grid = plan.geom.nout if which == 0 else plan.geom.nin
-    y = torch.empty((B, Cc) + tuple(grid), dtype=torch.float32, device=spec.device)
+    y = out if out is not None else torch.empty((B, Cc) + tuple(grid), dtype=torch.float32, device=spec.device)
     work = plan.workspace(B, Cc)
     check(_lib.lib().b2no_dft_inverse(plan.handle, which, _ptr(spec), _ptr(y), _ptr(work), B, Cc,
                                       math.prod(grid), C.byref(epi) if epi is not None else None, _stream()),
