@@ -35,9 +35,18 @@ struct b2no_tc_tables {
   int Ks, Qp, R;   // Ks = R * Qp, R = rows per 128-pixel tile, Qp = 2*K_last rounded up to 8
 };
 
+// operand images for the tensor-core forward-DFT kernel (tc_dft.cu), one per direction
+struct b2no_tc_fwd_tables {
+  float* tb;     // stage-1 B operand: [2 (hi, lo)][N1 x W] floats in the K-major core-matrix order, or nullptr (not eligible)
+  float* mimg;   // stage-2 A operand: [2 (hi, lo)][128][H] row-major; row kx = Re M[., kx], row 32 + kx = Im M[., kx]
+  int W, H, N1, Kx, Ky;
+};
+int b2no_tc_dft_forward(const b2no_plan* plan, int which, const float* x, float* spec, long planes, cudaStream_t st);
+
 struct b2no_plan {
   b2no_geom g;
   b2no_tc_tables tc[2];  // [0]: inverse on the nout grid, [1]: adjoint of the forward on the nin grid
+  b2no_tc_fwd_tables tcf[2];  // [0]: forward DFT on the nin grid, [1]: adjoint of the inverse on the nout grid
   int K[B2NO_MAX_DIM];   // kept modes per dim
   int device;
   // last-dim real tables, layout [qpad][npad] (q = 2k -> re, 2k+1 -> im), zero padded

@@ -228,6 +228,51 @@ extern "C" int b2no_plan_create(const b2no_geom* g, b2no_plan** out) {
     if ((rc = upload(&p->row_corner[j], rcorner))) return rc;
     if ((rc = upload(&p->row_local[j], rlocal))) return rc;
   }
+  // ---- tensor-core forward-DFT operand images (2-D; tc_dft.cu) --------------------------------
+  for (int which = 0; which < 2; which++) {
+    b2no_tc_fwd_tables& tf = p->tcf[which];
+    tf.tb = nullptr; tf.mimg = nullptr;
+    if (d != 2) continue;
+    const int Wd = which == 0 ? g->nin[1] : g->nout[1];
+    const int Hd = which == 0 ? g->nin[0] : g->nout[0];
+    if (which == 0 && (g->nin[0] != g->nfft[0] || g->nin[1] != g->nfft[1])) continue;   // crop / zero-pad (rno.py:66-67)
+    const int Kx = p->K[0], Ky = p->K[1];
+    if (Hd < 8 || Hd > 128 || 128 % Hd != 0 || Wd % 32 != 0 || Wd > 256 || Kx > 32 || 2 * Ky > 32) continue;
+    const int N1 = b2no_round_up(2 * Ky, 8);
+    tf.W = Wd; tf.H = Hd; tf.N1 = N1; tf.Kx = Kx; tf.Ky = Ky;
+    // stage 1: T[q][w] (q = 2 ky -> re, 2 ky + 1 -> im) = the last-dim real table of this direction
+    std::vector<float> tab_host((size_t)p->qpad * (which == 0 ? p->npad_in : p->npad_out));
+    B2NO_CHECK_CUDA(cudaMemcpy(tab_host.data(), which == 0 ? p->t_in : p->t_out, tab_host.size() * sizeof(float),
+                               cudaMemcpyDeviceToHost));
+    const int npad = which == 0 ? p->npad_in : p->npad_out;
+    std::vector<float> tb((size_t)2 * N1 * Wd, 0.f);
+    for (int q = 0; q < 2 * Ky; q++)
+      for (int w = 0; w < Wd; w++) {
+        const float v = tab_host[(size_t)q * npad + w];
+        const float hi = tf32_round_host(v);
+        // K-major, no swizzle: 8-row groups, 16-byte K chunks (tc.cuh::kmajor_off), in floats
+        const size_t off = (size_t)(q >> 3) * (Wd >> 2) * 32 + (size_t)(w >> 2) * 32 + (q & 7) * 4 + (w & 3);
+        tb[off] = hi;
+        tb[(size_t)N1 * Wd + off] = tf32_round_host(v - hi);
+      }
+    // stage 2: M[h][kx] complex (exp(-i) for both directions: m_fwd / m_adjinv), scale already in stage 1
+    std::vector<float2> m_host((size_t)Hd * Kx);
+    B2NO_CHECK_CUDA(cudaMemcpy(m_host.data(), which == 0 ? p->m_fwd[0] : p->m_adjinv[0], m_host.size() * sizeof(float2),
+                               cudaMemcpyDeviceToHost));
+    std::vector<float> mi((size_t)2 * 128 * Hd, 0.f);
+    for (int kx = 0; kx < Kx; kx++)
+      for (int h = 0; h < Hd; h++) {
+        const float2 m = m_host[(size_t)h * Kx + kx];
+        const float rh = tf32_round_host(m.x), ih = tf32_round_host(m.y);
+        mi[(size_t)kx * Hd + h] = rh;
+        mi[(size_t)(32 + kx) * Hd + h] = ih;
+        mi[(size_t)128 * Hd + (size_t)kx * Hd + h] = tf32_round_host(m.x - rh);
+        mi[(size_t)128 * Hd + (size_t)(32 + kx) * Hd + h] = tf32_round_host(m.y - ih);
+      }
+    int rc;
+    if ((rc = upload(&tf.tb, tb))) return rc;
+    if ((rc = upload(&tf.mimg, mi))) return rc;
+  }
   *out = p;
   return 0;
 }
@@ -238,6 +283,7 @@ extern "C" int b2no_plan_destroy(b2no_plan* p) {
   cudaFree(p->t_out);
   cudaFree(p->tc[0].timg);
   cudaFree(p->tc[1].timg);
+  for (int w = 0; w < 2; w++) { cudaFree(p->tcf[w].tb); cudaFree(p->tcf[w].mimg); }
   for (int j = 0; j < 2; j++) {
     cudaFree(p->m_fwd[j]); cudaFree(p->m_inv[j]); cudaFree(p->m_adjinv[j]); cudaFree(p->m_adjfwd[j]);
     cudaFree(p->row_corner[j]); cudaFree(p->row_local[j]);

@@ -180,6 +180,11 @@ extern "C" int b2no_dft_forward(const b2no_plan* p, int which, const float* x, f
   const int32_t* n = which == 0 ? p->g.nin : p->g.nout;
   const int Kl = p->K[d - 1];
   if (d == 1) return run_r2c(p, which, x, spec, bc, st);
+  if (d == 2) {
+    // tensor-core path (tc_dft.cu): one kernel, no intermediate, when the plane shape fits the 128-row tile
+    const int rc = b2no_tc_dft_forward(p, which, x, spec, (long)bc, st);
+    if (rc != 1) return rc;
+  }
   if (!work) return B2NO_E_ARG;
   float2* A = (float2*)work;
   if (d == 2) {
