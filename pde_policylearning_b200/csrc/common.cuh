@@ -38,7 +38,7 @@ struct b2no_tc_tables {
 // operand images for the tensor-core forward-DFT kernel (tc_dft.cu), one per direction
 struct b2no_tc_fwd_tables {
   float* tb;     // stage-1 B operand: [2 (hi, lo)][N1 x W] floats in the K-major core-matrix order, or nullptr (not eligible)
-  float* mimg;   // stage-2 A operand: [2 (hi, lo)][128][H] row-major; row kx = Re M[., kx], row 32 + kx = Im M[., kx]
+  float* mimg;   // stage-2 A operand, compact staging image: [2 (hi, lo)][2 Kx rows: Re M[., kx] then Im M[., kx]][H + 4]
   int W, H, N1, Kx, Ky;
 };
 int b2no_tc_dft_forward(const b2no_plan* plan, int which, const float* x, float* spec, long planes, cudaStream_t st);

@@ -269,9 +269,17 @@ extern "C" int b2no_plan_create(const b2no_geom* g, b2no_plan** out) {
         mi[(size_t)128 * Hd + (size_t)kx * Hd + h] = tf32_round_host(m.x - rh);
         mi[(size_t)128 * Hd + (size_t)(32 + kx) * Hd + h] = tf32_round_host(m.y - ih);
       }
+    // compact staging image of the same table for one bulk copy: [hi | lo][Re rows 0..Kx-1, Im rows 0..Kx-1][H + 4]
+    std::vector<float> ms((size_t)2 * 2 * Kx * (Hd + 4), 0.f);
+    for (int pass = 0; pass < 2; pass++)
+      for (int r = 0; r < 2 * Kx; r++)
+        for (int h = 0; h < Hd; h++) {
+          const int srow = r < Kx ? r : 32 + (r - Kx);
+          ms[((size_t)pass * 2 * Kx + r) * (Hd + 4) + h] = mi[(size_t)pass * 128 * Hd + (size_t)srow * Hd + h];
+        }
     int rc;
     if ((rc = upload(&tf.tb, tb))) return rc;
-    if ((rc = upload(&tf.mimg, mi))) return rc;
+    if ((rc = upload(&tf.mimg, ms))) return rc;
   }
   *out = p;
   return 0;

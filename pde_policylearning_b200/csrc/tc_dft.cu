@@ -14,10 +14,12 @@
 //   stage 2:  D2[128, N1] (per plane) = Mt[128 x H] (A operand, TMEM, constant: lane kx = Re M[., kx], lane 32 + kx = Im)
 //                                         x  A[N1 x H]^T (smem)
 //             Xh[kx, ky] = (D2[kx, 2ky] - D2[32+kx, 2ky+1]) + i (D2[kx, 2ky+1] + D2[32+kx, 2ky])
-// All products 3xTF32 (hi*hi + lo*hi + hi*lo).  Warp roles (320 threads, persistent CTAs, contiguous tile ranges):
-//   warp 0 TMA producer | warp 1 MMA issuer (stage 1 of tile t+1 is issued before stage 2 of tile t) |
-//   warps 2-5 converter | warps 6-9 epilogue (hand-over for tile t, then spectrum write-out of tile t-1)
-// HBM-bound by design: per plane the tensor pipe needs ~800 cycles, shared memory ~1100, HBM ~2900 (64 KB at 44 GB/s/SM).
+// All products 3xTF32 (hi*hi + lo*hi + hi*lo).  512 threads, persistent CTAs over contiguous tile ranges; warp roles are
+// listed at the kernel (two converter groups alternate K chunks; stage 1 of tile t+1 is issued before stage 2 of tile t;
+// hand-over and spectrum write-out run in different warps).  The constant Mt operand arrives by ONE bulk copy issued
+// ahead of the x stream.  HBM-bound by design: per plane the tensor pipe needs ~800 cycles, shared memory ~1100,
+// HBM ~2900 (64 KB at 44 GB/s/SM).  Measured (B200, cfg2, 134 MB): 37.6 us = 3.6 TB/s; 4.2 TB/s at 4x the batch.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -27,7 +29,7 @@ using namespace tc;
 
 namespace {
 
-constexpr int kThreadsFd = 320;
+constexpr int kThreadsFd = 512;
 constexpr uint32_t kB2Lbo = 144;            // bytes between K-adjacent core matrices of the stage-2 B operand (padded: no bank conflicts)
 constexpr uint32_t kB2Sbo = 32 * kB2Lbo;    // bytes between 8-row groups (128 lanes = 32 K chunks)
 
@@ -36,9 +38,10 @@ struct FdTc {
   long tiles, tiles_per_cta, planes;
   const float* tb; const float* mimg;
   float* spec;
+  int debug;   // ablation switches (B2NO_FD_DEBUG): 1 no converter TMEM stores, 2 no MMAs, 4 no hand-over stores, 8 no lo split
 };
 
-struct FdLayout { uint32_t tbh, tbl, b2, b2_bytes, xch, stages, bars, total; };
+struct FdLayout { uint32_t tbh, tbl, b2, b2_bytes, xch, mts, mts_stride, stages, bars, total; };
 
 __host__ __device__ inline FdLayout fd_layout(const FdTc& p) {
   FdLayout L;
@@ -49,6 +52,9 @@ __host__ __device__ inline FdLayout fd_layout(const FdTc& p) {
   o = (o + 127u) & ~127u;
   L.b2 = o; o += 4 * L.b2_bytes;                        // [buf 0/1][hi, lo]
   L.xch = o; o += 2u * p.R * 32 * p.N1 * 4;             // [buf 0/1][plane][kx][N1]: Im-row partial sums
+  L.mts_stride = (uint32_t)(p.H + 4) * 4;               // staging rows of the constant Mt operand, padded (no bank conflicts)
+  o = (o + 127u) & ~127u;
+  L.mts = o; o += 4u * p.Kx * L.mts_stride;             // [hi | lo][Re rows | Im rows], one bulk copy
   o = (o + 1023u) & ~1023u;
   L.stages = o; o += (uint32_t)p.S * 16384;
   L.bars = o; o += 8 * (2 * p.S + 20) + 16;
@@ -56,6 +62,19 @@ __host__ __device__ inline FdLayout fd_layout(const FdTc& p) {
   return L;
 }
 
+// debug: %globaltimer stamps of CTA 0 (B2NO_FD_DEBUG & 16), read back with b2no_debug_fd_ts
+__device__ unsigned long long g_fd_ts[16];
+__device__ __forceinline__ void fd_stamp(const FdTc& p, int slot) {
+  if ((p.debug & 16) && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_fd_ts[slot] = t;
+  }
+}
+
+// warp roles (16 warps; a warp may only touch TMEM lanes 32 * (warp % 4) .. + 31)
+//   0-3   converter A (even K chunks)      4-7  converter B (odd K chunks)      8-9  spectrum write-out (lanes 0-63)
+//   10    TMA producer                     11   MMA issuer                      12-15 hand-over D1 -> stage-2 B operand
 __global__ void __launch_bounds__(kThreadsFd, 1)
 k_fwd_tc(const __grid_constant__ CUtensorMap tmx, const FdTc p) {
   extern __shared__ uint8_t smem_raw[];
@@ -71,18 +90,18 @@ k_fwd_tc(const __grid_constant__ CUtensorMap tmx, const FdTc p) {
   uint64_t* b2_empty = b2_full + 2;
   uint64_t* d2_full = b2_empty + 2;
   uint64_t* d2_empty = d2_full + 2;
-  uint32_t* tslot = (uint32_t*)(d2_empty + 2);
+  uint64_t* mt_ready = d2_empty + 2;
+  uint64_t* mt_staged = mt_ready + 1;
+  uint32_t* tslot = (uint32_t*)(mt_staged + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N1 = p.N1, H = p.H, R = p.R, nk = p.nk;
+  if (tid == 0) fd_stamp(p, 0);
 
   // ---- one-time setup ----
   {
     const float4* src = (const float4*)p.tb;
     float4* dst = (float4*)(smem + L.tbh);
     for (int i = tid; i < 2 * N1 * p.W / 4; i += kThreadsFd) dst[i] = __ldg(src + i);
-    // zero the stage-2 B buffers once (pad rows q >= 2 Ky stay zero; the epilogue rewrites rows < N1 anyway)
-    float4* z = (float4*)(smem + L.b2);
-    for (uint32_t i = tid; i < 4 * L.b2_bytes / 16; i += kThreadsFd) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (tid == 0) {
     for (int s = 0; s < p.S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 128); }
@@ -92,24 +111,33 @@ k_fwd_tc(const __grid_constant__ CUtensorMap tmx, const FdTc p) {
       mbar_init(&b2_full[a], 128); mbar_init(&b2_empty[a], 1);
       mbar_init(&d2_full[a], 1); mbar_init(&d2_empty[a], 64);
     }
+    mbar_init(mt_ready, 128);
+    mbar_init(mt_staged, 1);
     fence_barrier_init();
   }
   fence_proxy_async();
-  if (warp == 1) tmem_alloc(tslot, 512);
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmx);
+  if (warp == 11) tmem_alloc(tslot, 512);
+  if (warp == 10 && lane == 0) tma_prefetch_desc(&tmx);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = *tslot;
+  if (tid == 0) fd_stamp(p, 1);
   // TMEM columns: [xa: 2 x (32 hi | 32 lo)] [d1: 2 x N1] [mt: H hi | H lo] [d2: 2 x R*N1]
   const uint32_t t_xa = tbase, t_d1 = tbase + 128u, t_mt = t_d1 + 2u * N1, t_d2 = t_mt + 2u * H;
   const long t_first = (long)blockIdx.x * p.tiles_per_cta;
   const long t_end = t_first + p.tiles_per_cta < p.tiles ? t_first + p.tiles_per_cta : p.tiles;
   const int ntiles = (int)(t_end > t_first ? t_end - t_first : 0);
+  const int quad = warp & 3;
+  const int m = quad * 32 + lane;                          // TMEM lane = tile row handled by this thread
+  const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
 
-  if (warp == 0) {
+  if (warp == 10) {
     // ===================== TMA producer: W/32 boxes [32 floats x 128 rows] per tile =====================
     if (lane == 0) {
+      // the constant stage-2 operand first (ahead of the x stream in the memory queues), one bulk copy
+      mbar_arrive_expect_tx(mt_staged, 4u * p.Kx * L.mts_stride);
+      bulk_load(smem + L.mts, p.mimg, 4u * p.Kx * L.mts_stride, mt_staged);
       long g = 0;
       for (int it = 0; it < ntiles; it++) {
         const long tile = t_first + it;
@@ -121,7 +149,7 @@ k_fwd_tc(const __grid_constant__ CUtensorMap tmx, const FdTc p) {
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 11) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = idesc_tf32(128, N1, 0, 0);
     const uint32_t sbase = smem_u32(smem);
@@ -138,7 +166,7 @@ k_fwd_tc(const __grid_constant__ CUtensorMap tmx, const FdTc p) {
         if (elect_one()) {
           const uint32_t d = t_d1 + (uint32_t)db * N1;
           const uint32_t xa = t_xa + 64u * xb;
-          for (int pass = 0; pass < 3; pass++) {
+          for (int pass = 0; pass < ((p.debug & 2) ? 0 : 3); pass++) {
             const uint32_t ac = pass == 1 ? xa + 32 : xa;
             const uint64_t dt = (pass == 2 ? d_tl : d_th) + (uint64_t)(c * 64);     // 32 K elements = 8 chunks of 128 B
 #pragma unroll
@@ -175,59 +203,73 @@ k_fwd_tc(const __grid_constant__ CUtensorMap tmx, const FdTc p) {
     };
     for (int it = 0; it < ntiles; it++) {
       stage1(it);
+      if (it == 1) { mbar_wait(mt_ready, 0); tc_fence_after(); }
       if (it > 0) stage2(it - 1);
     }
+    if (ntiles == 1) { mbar_wait(mt_ready, 0); tc_fence_after(); }
     if (ntiles > 0) stage2(ntiles - 1);
-  } else if (warp < 6) {
-    // ===================== converter: thread = row; shared memory (swizzled box) -> TMEM A operand =====================
-    const int quad = warp & 3;
-    const int m = quad * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    // constant stage-2 A operand (Mt hi | lo), once
-    for (int c0 = 0; c0 < H; c0 += 8) {
-      float hi[8], lo[8];
+  } else if (warp < 8) {
+    // ===================== converters: thread = row; shared memory (swizzled box) -> TMEM A operand =====================
+    // group A (warps 0-3) takes the even chunks / TMEM buffer 0, group B (warps 4-7) the odd chunks / buffer 1
+    const int grp = warp >> 2;
+    const long total = (long)ntiles * nk;
+    for (long g = grp; g < total; g += 2) {
+      const int s = (int)(g % p.S);
+      mbar_wait(&full[s], (uint32_t)(g / p.S) & 1u);
+      if (g == 0 && tid == 0) fd_stamp(p, 2);
+      const uint8_t* row = smem + L.stages + (size_t)s * 16384 + (size_t)m * 128;
+      float hi[32], lo[32];
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        hi[j] = __ldg(p.mimg + (size_t)m * H + c0 + j);
-        lo[j] = __ldg(p.mimg + (size_t)128 * H + (size_t)m * H + c0 + j);
-      }
-      tmem_st8(t_mt + lane_base + c0, hi);
-      tmem_st8(t_mt + lane_base + H + c0, lo);
-    }
-    tmem_st_wait();
-    long g = 0;
-    for (int it = 0; it < ntiles; it++) {
-      for (int c = 0; c < nk; c++, g++) {
-        const int s = (int)(g % p.S);
-        const int xb = (int)(g & 1);
-        mbar_wait(&full[s], (uint32_t)(g / p.S) & 1u);
-        const uint8_t* row = smem + L.stages + (size_t)s * 16384 + (size_t)m * 128;
-        float hi[32], lo[32];
+      for (int i = 0; i < 8; i++)
+        *reinterpret_cast<float4*>(hi + 4 * i) = *reinterpret_cast<const float4*>(row + ((i ^ (m & 7)) << 4));
+      mbar_arrive(&empty[s]);
 #pragma unroll
-        for (int i = 0; i < 8; i++)
-          *reinterpret_cast<float4*>(hi + 4 * i) = *reinterpret_cast<const float4*>(row + ((i ^ (m & 7)) << 4));
-        mbar_arrive(&empty[s]);
-#pragma unroll
-        for (int i = 0; i < 32; i++) lo[i] = tf32_lo(hi[i]);
-        mbar_wait(&xa_empty[xb], ((uint32_t)(g >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t xa = t_xa + lane_base + 64u * xb;
+      for (int i = 0; i < 32; i++) lo[i] = tf32_lo(hi[i]);
+      mbar_wait(&xa_empty[grp], ((uint32_t)(g >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t xa = t_xa + lane_base + 64u * grp;
+      if (!(p.debug & 1)) {
         tmem_st16(xa, hi); tmem_st16(xa + 16, hi + 16);
         tmem_st16(xa + 32, lo); tmem_st16(xa + 48, lo + 16);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&xa_full[xb]);
       }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&xa_full[grp]);
+      if (g == 0 && tid == 0) fd_stamp(p, 3);
     }
-  } else {
-    // ===================== epilogue: hand-over D1 -> stage-2 B operand; spectrum write-out =====================
-    const int quad = warp & 3;                 // warps 6,7,8,9 -> TMEM lane quadrants 2,3,0,1
-    const int m = quad * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    const int Ky = p.Ky, Kx = p.Kx;
-    auto handover = [&](int it) {
+  } else if (warp >= 12) {
+    // ===================== hand-over: D1 (TMEM) -> hi/lo K-major B operand of stage 2 (shared memory) =====================
+    // first, once: the constant stage-2 A operand Mt.  Rows kx (Re) and 32 + kx (Im) are staged through shared memory
+    // with coalesced loads (one L2 round trip per pass), then every thread moves ITS lane's row into TMEM.
+    {
+      const int Kx = p.Kx;
+      float* mts = (float*)(smem + L.mts);
+      const int rs = (int)(L.mts_stride / 4);
+      mbar_wait(mt_staged, 0);
+      const int r = m < Kx ? m : ((m >= 32 && m < 32 + Kx) ? Kx + (m - 32) : -1);
+      for (int pass = 0; pass < 2; pass++) {
+        const float* src = mts + (size_t)pass * 2 * Kx * rs;
+        for (int c0 = 0; c0 < H; c0 += 8) {
+          float v[8];
+          if (r >= 0) {
+            *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(src + (size_t)r * rs + c0);
+            *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(src + (size_t)r * rs + c0 + 4);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = 0.f;
+          }
+          tmem_st8(t_mt + lane_base + (uint32_t)(pass * H + c0), v);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(mt_ready);
+      if (tid == 12 * 32) fd_stamp(p, 4);
+    }
+    for (int it = 0; it < ntiles; it++) {
       const int db = it & 1;
       mbar_wait(&d1_full[db], (uint32_t)(it >> 1) & 1u);
+      if (it == 0 && tid == 12 * 32) fd_stamp(p, 5);
       tc_fence_after();
       float v[32];
 #pragma unroll
@@ -242,7 +284,7 @@ k_fwd_tc(const __grid_constant__ CUtensorMap tmx, const FdTc p) {
       const uint32_t koff = (uint32_t)(m >> 2) * kB2Lbo + (uint32_t)(m & 3) * 4;
 #pragma unroll
       for (int q = 0; q < 32; q++) {
-        if (q < N1) {
+        if (q < N1 && !(p.debug & 4)) {
           const uint32_t off = (uint32_t)(q >> 3) * kB2Sbo + (uint32_t)(q & 7) * 16 + koff;
           *(float*)(bh + off) = v[q];
           *(float*)(bl + off) = tf32_lo(v[q]);
@@ -250,13 +292,17 @@ k_fwd_tc(const __grid_constant__ CUtensorMap tmx, const FdTc p) {
       }
       fence_proxy_async();
       mbar_arrive(&b2_full[db]);
-    };
-    auto writeout = [&](int it) {
-      if (quad > 1) return;
+      if (it == 0 && tid == 12 * 32) fd_stamp(p, 6);
+    }
+  } else {
+    // ===================== spectrum write-out (warps 8, 9 = TMEM lanes 0-31 Re rows, 32-63 Im rows) =====================
+    const int Ky = p.Ky, Kx = p.Kx;
+    for (int it = 0; it < ntiles; it++) {
       const int db = it & 1;
       const long tile = t_first + it;
       float* xch = (float*)(smem + L.xch) + (size_t)db * R * 32 * N1;
       mbar_wait(&d2_full[db], (uint32_t)(it >> 1) & 1u);
+      if (it == 0 && tid == 256) fd_stamp(p, 7);
       tc_fence_after();
       if (quad == 1) {
         // Im rows: lane kx holds sum_h Im M[h, kx] * (A re | A im)
@@ -293,19 +339,20 @@ k_fwd_tc(const __grid_constant__ CUtensorMap tmx, const FdTc p) {
         tc_fence_before();
         mbar_arrive(&d2_empty[db]);
       }
-    };
-    for (int it = 0; it < ntiles; it++) {
-      handover(it);
-      if (it > 0) writeout(it - 1);
     }
-    if (ntiles > 0) writeout(ntiles - 1);
+    if (tid == 256) fd_stamp(p, 8);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tbase, 512);
+  if (warp == 11) tmem_dealloc(tbase, 512);
+  if (tid == 0) fd_stamp(p, 9);
 }
 
 }  // namespace
+
+extern "C" int b2no_debug_fd_ts(unsigned long long* host16) {
+  return (int)cudaMemcpyFromSymbol(host16, g_fd_ts, sizeof(unsigned long long) * 16);
+}
 
 void b2no_tc_count_launch();
 
@@ -322,6 +369,7 @@ int b2no_tc_dft_forward(const b2no_plan* plan, int which, const float* x, float*
   const long rows = planes * tf.H;
   p.tiles = (rows + 127) / 128;
   p.tb = tf.tb; p.mimg = tf.mimg; p.spec = spec;
+  { const char* dbg = getenv("B2NO_FD_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
   if (128u + 2u * p.N1 + 2u * p.H + 2u * p.R * p.N1 > 512u) return 1;
   int dev = 0, max_smem = 0;
   B2NO_CHECK_CUDA(cudaGetDevice(&dev));

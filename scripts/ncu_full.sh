@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 for what in "$@"; do
   case $what in
     mlp)   k="k_mlp_tc"; skip=2; cnt=2;;
-    fwd)   k="k_r2c_last|k_cmat|k_fwd_tc"; skip=2; cnt=2;;
+    fwd)   k="k_r2c_last|k_cmat|k_fwd_tc"; skip=1; cnt=1;;
     inv)   k="k_pw_tc|k_inv_h"; skip=2; cnt=2;;
     invgelu) k="k_pw_tc"; skip=1; cnt=1;;
     wgrad) k="k_wgrad_tc"; skip=1; cnt=1;;

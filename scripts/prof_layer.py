@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from pde_policylearning_b200 import ops
 
-B, C, N, M = 64, 32, 128, 12
+import os as _os
+B, C, N, M = int(_os.environ.get("PROF_B", "64")), 32, 128, 12
 dev = torch.device("cuda", 0)
 plan = ops.get_plan(ops.SpecGeom(nin=(N, N), half=(M // 2, M // 2), norm="forward"), dev)
 x = torch.randn(B, C, N, N, device=dev)
