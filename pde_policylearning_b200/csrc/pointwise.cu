@@ -162,15 +162,35 @@ k_pw_wgrad(const float* __restrict__ g, const float* __restrict__ x, float* __re
   }
 }
 
-__global__ void k_pw_wgrad_reduce(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ db,
-                                  int nblk, int Ci, int Co) {
+// Deterministic sum of the per-CTA partials: a block owns 32 consecutive outputs; its 8 warps split the partials
+// (each warp reads 128 contiguous bytes per partial, 4 independent loads in flight), then combine through shared memory
+// in a fixed order.  (The one-thread-per-output loop it replaces was a 148-deep dependent load chain: 13 us.)
+__global__ void __launch_bounds__(256)
+k_pw_wgrad_reduce(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ db, int nblk, int Ci, int Co) {
+  __shared__ float red[8][33];
   const int n = Co * Ci + Co;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  float s = 0.f;
-  for (int b = 0; b < nblk; b++) s += partial[(size_t)b * n + idx];
-  if (idx < Co * Ci) dw[idx] = s;
-  else if (db) db[idx - Co * Ci] = s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + lane;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (idx < n) {
+    int b = warp;
+    for (; b + 24 < nblk; b += 32) {
+      s0 += __ldg(partial + (size_t)b * n + idx);
+      s1 += __ldg(partial + (size_t)(b + 8) * n + idx);
+      s2 += __ldg(partial + (size_t)(b + 16) * n + idx);
+      s3 += __ldg(partial + (size_t)(b + 24) * n + idx);
+    }
+    for (; b < nblk; b += 8) s0 += __ldg(partial + (size_t)b * n + idx);
+  }
+  red[warp][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (warp == 0 && idx < n) {
+    float s = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; w8++) s += red[w8][lane];
+    if (idx < Co * Ci) dw[idx] = s;
+    else if (db) db[idx - Co * Ci] = s;
+  }
 }
 
 static void wgrad_cfg(int ci, int co, int* tiles_i, int* tiles_o, int* o_per_block, int* gy) {
@@ -201,7 +221,7 @@ extern "C" int b2no_pw_wgrad(const float* g, const float* x, float* dw, float* d
     const int rc = b2no_tc_wgrad(g, x, partial, wgrad_blocks_x(), batch, ci, co, pixels, &nblk, st);
     if (rc == 0) {
       const int n = co * ci + co;
-      k_pw_wgrad_reduce<<<(n + 255) / 256, 256, 0, st>>>(partial, dw, db, nblk, ci, co);
+      k_pw_wgrad_reduce<<<(n + 31) / 32, 256, 0, st>>>(partial, dw, db, nblk, ci, co);
       B2NO_LAUNCH_CHECK();
       return 0;
     }
@@ -226,7 +246,7 @@ extern "C" int b2no_pw_wgrad(const float* g, const float* x, float* dw, float* d
   k_pw_wgrad<<<grid, 256, smem, st>>>(g, x, partial, batch, ci, co, pixels, opb, tiles_o, tiles_i, db ? 1 : 0);
   B2NO_LAUNCH_CHECK();
   const int n = co * ci + co;
-  k_pw_wgrad_reduce<<<(n + 255) / 256, 256, 0, st>>>(partial, dw, db, (int)bx, ci, co);
+  k_pw_wgrad_reduce<<<(n + 31) / 32, 256, 0, st>>>(partial, dw, db, (int)bx, ci, co);
   B2NO_LAUNCH_CHECK();
   return 0;
 }

@@ -402,12 +402,29 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
   if (warp == 1) tmem_dealloc(tbase, ncols);
 }
 
-__global__ void k_sum_partials(const float* __restrict__ partial, float* __restrict__ out, int nblk, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float s = 0.f;
-  for (int b = 0; b < nblk; b++) s += partial[(size_t)b * n + i];
-  out[i] = s;
+// deterministic sum of per-CTA partials: block = 32 outputs x 8 warps over the partials, fixed combine order
+__global__ void __launch_bounds__(256)
+k_sum_partials(const float* __restrict__ partial, float* __restrict__ out, int nblk, int n) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + lane;
+  float s0 = 0.f, s1 = 0.f;
+  if (idx < n) {
+    int b = warp;
+    for (; b + 8 < nblk; b += 16) {
+      s0 += __ldg(partial + (size_t)b * n + idx);
+      s1 += __ldg(partial + (size_t)(b + 8) * n + idx);
+    }
+    for (; b < nblk; b += 8) s0 += __ldg(partial + (size_t)b * n + idx);
+  }
+  red[warp][lane] = s0 + s1;
+  __syncthreads();
+  if (warp == 0 && idx < n) {
+    float s = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; w8++) s += red[w8][lane];
+    out[idx] = s;
+  }
 }
 
 int mlp_launch(MlpTc& p, const float* x, int batch, long pixels, cudaStream_t st, int* grid_out) {
@@ -509,7 +526,7 @@ extern "C" int b2no_mlp_head_bwd(const float* x, const float* w1, const float* b
   if (rc == 1) return B2NO_E_UNSUPPORTED;
   if (rc) return rc;
   b2no_tc_count_launch();
-  k_sum_partials<<<(hidden + 255) / 256, 256, 0, st>>>(partial, dw2, grid, hidden);
+  k_sum_partials<<<(hidden + 31) / 32, 256, 0, st>>>(partial, dw2, grid, hidden);
   B2NO_LAUNCH_CHECK();
   return 0;
 }

@@ -366,22 +366,27 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
 // A'[b][row][q/4][n/8][n%8][q%4] (hi and lo) from the kept spectrum: the second-to-last inverse stage.
 //   S[b,o,h,ky] = sum_kx M[kx][h] * spec[b][o][kx][ky];   q = 2 ky -> Re S, 2 ky + 1 -> Im S
 // One block per (sample, group of HB rows): the sample's spectrum is staged in shared memory once.
-constexpr int kInvHB = 8;
+constexpr int kInvHB = 32;
 __global__ void __launch_bounds__(256)
 k_inv_h(const float2* __restrict__ spec, const float2* __restrict__ M, float* __restrict__ ahi, float* __restrict__ alo,
         int Co, int Np, int Kx, int H, int Ky, int Qp) {
-  extern __shared__ float2 s_spec[];  // [Co][Kx*Ky + 1]
+  extern __shared__ float2 s_spec[];  // [Co][Kx*Ky + 1] then the M rows of this block [Kx][kInvHB]
   const int b = blockIdx.y, h0 = blockIdx.x * kInvHB;
   const int kk = Kx * Ky, stride = kk + 1;
+  float2* s_m = s_spec + (size_t)Co * stride;
   const float2* sp = spec + (size_t)b * Co * kk;
-  for (int i = threadIdx.x; i < Co * kk; i += blockDim.x) {
-    const int o = i / kk, r = i - o * kk;
-    s_spec[o * stride + r] = sp[i];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = warp; o < Co; o += 8)
+    for (int r = lane; r < kk; r += 32) s_spec[o * stride + r] = __ldg(sp + (size_t)o * kk + r);
+  for (int i = threadIdx.x; i < Kx * kInvHB; i += 256) {
+    const int kx = i / kInvHB, hl = i - kx * kInvHB;
+    s_m[i] = (h0 + hl < H) ? __ldg(M + (size_t)kx * H + h0 + hl) : make_float2(0.f, 0.f);
   }
   __syncthreads();
   const int ng = Np >> 3, nq = Qp >> 2;
-  const int per_row = nq * ng * 16;
-  for (int idx = threadIdx.x; idx < kInvHB * per_row; idx += blockDim.x) {
+  const int per_row = nq * ng * 16;                    // (kq, og, o8, l0): 2 floats each
+  // thread -> fixed (kq, og, o8, l0) when per_row divides 256 or vice versa; rows advance by 256 / per_row
+  for (int idx = threadIdx.x; idx < kInvHB * per_row; idx += 256) {
     const int hl = idx / per_row;
     int r = idx - hl * per_row;
     const int h = h0 + hl;
@@ -393,8 +398,9 @@ k_inv_h(const float2* __restrict__ spec, const float2* __restrict__ M, float* __
     float sr = 0.f, si = 0.f;
     if (o < Co && ky < Ky) {
       const float2* so = s_spec + o * stride + ky;
+#pragma unroll 4
       for (int kx = 0; kx < Kx; kx++) {
-        const float2 m = __ldg(M + (size_t)kx * H + h);
+        const float2 m = s_m[kx * kInvHB + hl];
         const float2 v = so[kx * Ky];
         sr = fmaf(m.x, v.x, fmaf(-m.y, v.y, sr));
         si = fmaf(m.x, v.y, fmaf(m.y, v.x, si));
@@ -496,7 +502,7 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
   if (spec) {
     const int32_t* n = which == 0 ? plan->g.nout : plan->g.nin;
     const float2* M = which == 0 ? plan->m_inv[0] : plan->m_adjfwd[0];
-    const size_t smem = (size_t)channels * (plan->K[0] * plan->K[1] + 1) * sizeof(float2);
+    const size_t smem = ((size_t)channels * (plan->K[0] * plan->K[1] + 1) + (size_t)plan->K[0] * kInvHB) * sizeof(float2);
     if (smem > 200 * 1024) return 1;
     if (smem > 48 * 1024) B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_inv_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((n[0] + kInvHB - 1) / kInvHB), (unsigned)batch);

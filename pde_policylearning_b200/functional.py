@@ -97,6 +97,89 @@ def spectral_block(x, corners: Sequence[torch.Tensor], geom: SpecGeom, bias=None
     return SpectralBlockFn.apply(x, bias, pw_weight, geom, act, *corners)
 
 
+class FNOStackFn(torch.autograd.Function):
+    """n_layers x [ y = act_l( spectral_conv_l(x) + bias_l + skip_l x ) ] as ONE autograd node (FNO.forward's loop over
+    FNOBlocks, tfno.py:203-204 + fno_block.py:131-150).  Same kernels as SpectralBlockFn, but the backward chains the
+    layers: the dx pass of layer l multiplies by act'(z_{l-1}) in its epilogue and so emits gz_{l-1} directly -- no
+    separate activation-backward pass over the activations.
+
+    params = for each layer: bias (Co,) | pw_w (Co, Ci, 1...) | n_corners corner tensors."""
+
+    @staticmethod
+    def forward(ctx, x, geom: SpecGeom, acts, n_corners, *params):
+        ops._require_cuda(x)
+        x = _contig(x.float())
+        plan = get_plan(geom, x.device)
+        per = 2 + n_corners
+        L = len(params) // per
+        need_grad = any(ctx.needs_input_grad)
+        saved, meta = [], []
+        cur = x
+        for l in range(L):
+            bias, pw_w = params[l * per], params[l * per + 1]
+            det = [c.detach() for c in params[l * per + 2:(l + 1) * per]]
+            B, ci = cur.shape[:2]
+            co = det[0].shape[1]
+            xh = ops.dft_forward(plan, 0, cur)
+            yh = ops.mix(plan, 0, xh, det, ci, co)
+            act = acts[l]
+            need_z = act not in (None, "none") and need_grad
+            z = torch.empty((B, co) + tuple(plan.geom.nout), dtype=torch.float32, device=x.device) if need_z else None
+            pw2d = _contig(pw_w.detach().reshape(pw_w.shape[0], -1).float())
+            epi = ops.make_epilogue(bias=_contig(bias.detach().reshape(-1).float()), pw_w=pw2d, pw_x=cur, preact=z, act=act)
+            y = ops.dft_inverse(plan, 0, yh, epi)
+            saved += [cur, xh, z if z is not None else cur.new_empty(0), pw2d] + det
+            meta.append((tuple(bias.shape), tuple(pw_w.shape), ci, co, need_z))
+            cur = y
+        ctx.geom, ctx.acts, ctx.n_corners, ctx.meta = geom, acts, n_corners, meta
+        ctx.save_for_backward(*saved)
+        return cur
+
+    @staticmethod
+    def backward(ctx, gy):
+        geom, acts, nc, meta = ctx.geom, ctx.acts, ctx.n_corners, ctx.meta
+        saved = ctx.saved_tensors
+        per_s = 4 + nc
+        L = len(meta)
+        plan = get_plan(geom, gy.device)
+        per = 2 + nc
+        grads = [None] * (L * per)
+        g = _contig(gy.float())
+        # top layer: gradient w.r.t. its pre-activation
+        if meta[L - 1][4]:
+            g = ops.act_bwd(g, saved[(L - 1) * per_s + 2], acts[L - 1])
+        for l in range(L - 1, -1, -1):
+            x, xh, _, pw2d = saved[l * per_s: l * per_s + 4]
+            det = list(saved[l * per_s + 4: (l + 1) * per_s])
+            bias_shape, pw_shape, ci, co, _ = meta[l]
+            need = ctx.needs_input_grad[4 + l * per: 4 + (l + 1) * per]
+            gyh = ops.dft_forward(plan, 1, g)
+            if any(need[2:]):
+                dcs = ops.mix_dw(plan, xh, gyh, det, needs_zero=_geom_has_overlap(geom))
+                for j in range(nc):
+                    grads[l * per + 2 + j] = dcs[j]
+            if need[0] or need[1]:
+                dpw, db = ops.pw_wgrad(g, x, need_bias=need[0])
+                grads[l * per + 1] = dpw.reshape(pw_shape)
+                if need[0]:
+                    grads[l * per] = db.reshape(bias_shape)
+            if l > 0 or ctx.needs_input_grad[0]:
+                gxh = ops.mix(plan, 1, gyh, det, ci, co)
+                zprev = saved[(l - 1) * per_s + 2] if (l > 0 and meta[l - 1][4]) else None
+                epi = ops.make_epilogue(pw_w=pw2d, pw_x=g, pw_transposed=True, dact_z=zprev,
+                                        dact=acts[l - 1] if zprev is not None else None)
+                g = ops.dft_inverse(plan, 1, gxh, epi)
+        return (g if ctx.needs_input_grad[0] else None, None, None, None) + tuple(grads)
+
+
+def fno_stack(x, geom: SpecGeom, layers, acts):
+    """layers: list of (bias, pw_weight, [corners]); acts: activation name (or None) per layer."""
+    flat = []
+    for bias, pw_w, corners in layers:
+        flat += [bias, pw_w] + list(corners)
+    return FNOStackFn.apply(x, geom, tuple(acts), len(layers[0][2]), *flat)
+
+
 class PointwiseConvFn(torch.autograd.Function):
     """y = act(W x + b), channels-first 1x1 convolution (tfno.py:11-38 Lifting / Projection convs,
     skip_connections.py:31)."""

@@ -376,8 +376,18 @@ class FNO(nn.Module):
 
     def forward(self, x):
         x = self.lifting(x)
-        for layer_idx in range(self.n_layers):
-            x = self.fno_blocks(x, layer_idx)
+        blocks = self.fno_blocks
+        if (isinstance(blocks, FNOBlocks) and hasattr(blocks.convs, "forward_fused") and blocks.convs.bias is not None
+                and blocks.convs.output_scaling_factor is None and x.dim() == 2 + blocks.convs.order):
+            # the whole stack as one autograd node: the backward chains act'(z) into the dx epilogues
+            convs = blocks.convs
+            geom = convs._geom(tuple(x.shape[2:]), 0)
+            acts = [(_act_name(blocks.non_linearity) if i < (blocks.n_layers - i) else None) for i in range(self.n_layers)]
+            layers = [(convs.bias[i].reshape(-1), blocks.fno_skips[i].weight, convs.corners(i)) for i in range(self.n_layers)]
+            x = Fn.fno_stack(x, geom, layers, acts)
+        else:
+            for layer_idx in range(self.n_layers):
+                x = self.fno_blocks(x, layer_idx)
         return self.projection(x)
 
     @property

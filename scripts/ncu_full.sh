@@ -9,8 +9,9 @@ for what in "$@"; do
     inv)   k="k_pw_tc|k_inv_h"; skip=2; cnt=2;;
     invgelu) k="k_pw_tc"; skip=1; cnt=1;;
     wgrad) k="k_wgrad_tc"; skip=1; cnt=1;;
+    invh)  k="k_inv_h"; skip=1; cnt=1; what2=inv;;
   esac
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$k" -s $skip -c $cnt -f -o gpurun_out/${tag}_${what} \
-      python scripts/prof_layer.py $what 2 > gpurun_out/${tag}_${what}.log 2>&1
+      python scripts/prof_layer.py ${what2:-$what} 2 > gpurun_out/${tag}_${what}.log 2>&1
   echo "$what exit $?"
 done
