@@ -82,7 +82,7 @@ template <int MODE>
 __device__ __forceinline__ float epi_value(float z, float mulv, float dzv, int act, int dact) {
   if (MODE == 1) return z;
   if (MODE == 2) return b2no_act(z, B2NO_ACT_GELU);
-  if (MODE == 3) return z * b2no_act_grad(dzv, B2NO_ACT_GELU);
+  if (MODE == 3) return z * dzv;   // dzv already holds GELU'(dz) (packed evaluation in the epilogue)
   float v = b2no_act(z, act) * mulv;
   if (dact) v *= b2no_act_grad(dzv, dact);
   return v;
@@ -302,6 +302,14 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
       const int b = (int)(tile / p.tiles_per_img);
       const long px = (tile - (long)b * p.tiles_per_img) * 128 + t;
       const size_t base = (size_t)b * p.Co * p.P + px;
+      // MODE 3: the saved pre-activations of the layer below are fetched BEFORE waiting for the accumulator, so the
+      // global-load latency overlaps the MMAs of this tile instead of following them
+      float dvn[16];
+      if (MODE == 3) {
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+          dvn[j] = (half * 16 + j < p.Co) ? __ldg(p.dz + base + (size_t)(half * 16 + j) * p.P) : 0.f;
+      }
       mbar_wait(&acc_full[a], aph);
       tc_fence_after();
       for (int c0 = half * 16; c0 < p.Co; c0 += 32) {
@@ -331,8 +339,19 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
         } else {
           float dv[16];
           if (MODE == 3) {
+            if (c0 == half * 16) {
 #pragma unroll
-            for (int j = 0; j < 16; j++) dv[j] = (c0 + j < p.Co) ? __ldg(p.dz + base + (size_t)(c0 + j) * p.P) : 0.f;
+              for (int j = 0; j < 16; j++) dv[j] = dvn[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; j++) dv[j] = (c0 + j < p.Co) ? __ldg(p.dz + base + (size_t)(c0 + j) * p.P) : 0.f;
+            }
+            // packed GELU' (two channels per FMA-pipe instruction)
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              const float2 gg = b2no_gelu2_grad(make_float2(dv[j], dv[j + 1]));
+              dv[j] = gg.x; dv[j + 1] = gg.y;
+            }
           }
           float bv[16];
 #pragma unroll
@@ -367,6 +386,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
 //   S[b,o,h,ky] = sum_kx M[kx][h] * spec[b][o][kx][ky];   q = 2 ky -> Re S, 2 ky + 1 -> Im S
 // One block per (sample, group of HB rows): the sample's spectrum is staged in shared memory once.
 constexpr int kInvHB = 32;
+template <int KXM>   // compile-time bound on the kept rows Kx (register array size)
 __global__ void __launch_bounds__(256)
 k_inv_h(const float2* __restrict__ spec, const float2* __restrict__ M, float* __restrict__ ahi, float* __restrict__ alo,
         int Co, int Np, int Kx, int H, int Ky, int Qp) {
@@ -385,31 +405,35 @@ k_inv_h(const float2* __restrict__ spec, const float2* __restrict__ M, float* __
   __syncthreads();
   const int ng = Np >> 3, nq = Qp >> 2;
   const int per_row = nq * ng * 16;                    // (kq, og, o8, l0): 2 floats each
-  // thread -> fixed (kq, og, o8, l0) when per_row divides 256 or vice versa; rows advance by 256 / per_row
-  for (int idx = threadIdx.x; idx < kInvHB * per_row; idx += 256) {
-    const int hl = idx / per_row;
-    int r = idx - hl * per_row;
-    const int h = h0 + hl;
-    if (h >= H) break;
-    const int l0 = r & 1, o8 = (r >> 1) & 7;
-    r >>= 4;
+  const int rows = H - h0 < kInvHB ? H - h0 : kInvHB;
+  // a thread owns one (kq, og, o8, l0) output slot: its Kx spectrum values do not depend on the row, so they are
+  // read once into registers and every row costs Kx x (one broadcast LDS of M + 4 FMA)
+  for (int e = threadIdx.x; e < per_row; e += 256) {
+    const int l0 = e & 1, o8 = (e >> 1) & 7;
+    const int r = e >> 4;
     const int og = r % ng, kq = r / ng;
     const int ky = kq * 2 + l0, o = og * 8 + o8;
-    float sr = 0.f, si = 0.f;
-    if (o < Co && ky < Ky) {
-      const float2* so = s_spec + o * stride + ky;
-#pragma unroll 4
-      for (int kx = 0; kx < Kx; kx++) {
-        const float2 m = s_m[kx * kInvHB + hl];
-        const float2 v = so[kx * Ky];
-        sr = fmaf(m.x, v.x, fmaf(-m.y, v.y, sr));
-        si = fmaf(m.x, v.y, fmaf(m.y, v.x, si));
+    const bool valid = o < Co && ky < Ky;
+    float2 v[KXM];
+#pragma unroll
+    for (int kx = 0; kx < KXM; kx++)
+      v[kx] = (valid && kx < Kx) ? s_spec[o * stride + kx * Ky + ky] : make_float2(0.f, 0.f);
+    const size_t off0 = ((size_t)b * H + h0) * Qp * Np + (size_t)kq * ng * 32 + og * 32 + o8 * 4 + l0 * 2;
+    for (int hl = 0; hl < rows; hl++) {
+      float sr = 0.f, si = 0.f;
+#pragma unroll
+      for (int kx = 0; kx < KXM; kx++) {
+        if (kx < Kx) {
+          const float2 m = s_m[kx * kInvHB + hl];
+          sr = fmaf(m.x, v[kx].x, fmaf(-m.y, v[kx].y, sr));
+          si = fmaf(m.x, v[kx].y, fmaf(m.y, v[kx].x, si));
+        }
       }
+      const size_t off = off0 + (size_t)hl * Qp * Np;
+      const float hr = tf32_rna(sr), hi = tf32_rna(si);
+      *reinterpret_cast<float2*>(ahi + off) = make_float2(hr, hi);
+      *reinterpret_cast<float2*>(alo + off) = make_float2(tf32_rna(sr - hr), tf32_rna(si - hi));
     }
-    const size_t off = ((size_t)b * H + h) * Qp * Np + (size_t)kq * ng * 32 + og * 32 + o8 * 4 + l0 * 2;
-    const float hr = tf32_rna(sr), hi = tf32_rna(si);
-    *reinterpret_cast<float2*>(ahi + off) = make_float2(hr, hi);
-    *reinterpret_cast<float2*>(alo + off) = make_float2(tf32_rna(sr - hr), tf32_rna(si - hi));
   }
 }
 
@@ -504,10 +528,21 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
     const float2* M = which == 0 ? plan->m_inv[0] : plan->m_adjfwd[0];
     const size_t smem = ((size_t)channels * (plan->K[0] * plan->K[1] + 1) + (size_t)plan->K[0] * kInvHB) * sizeof(float2);
     if (smem > 200 * 1024) return 1;
-    if (smem > 48 * 1024) B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_inv_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((n[0] + kInvHB - 1) / kInvHB), (unsigned)batch);
-    k_inv_h<<<grid, 256, smem, st>>>((const float2*)spec, M, (float*)p.ahi, (float*)p.alo, channels, p.Np, plan->K[0], n[0],
-                                     plan->K[1], p.Qp);
+#define INVH_LAUNCH(KXM)                                                                                                \
+  do {                                                                                                                  \
+    if (smem > 48 * 1024) B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_inv_h<KXM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_inv_h<KXM><<<grid, 256, smem, st>>>((const float2*)spec, M, (float*)p.ahi, (float*)p.alo, channels, p.Np, plan->K[0], n[0], \
+                                          plan->K[1], p.Qp);                                                            \
+  } while (0)
+    const int kx = plan->K[0];
+    if (kx <= 8) INVH_LAUNCH(8);
+    else if (kx <= 12) INVH_LAUNCH(12);
+    else if (kx <= 16) INVH_LAUNCH(16);
+    else if (kx <= 24) INVH_LAUNCH(24);
+    else if (kx <= 32) INVH_LAUNCH(32);
+    else return 1;
+#undef INVH_LAUNCH
     B2NO_LAUNCH_CHECK();
   }
   const bool extras = p.add || p.mul;
