@@ -24,7 +24,10 @@ using namespace tc;
 
 namespace {
 
-constexpr int kThreadsMlp = 448;
+constexpr int kEW = 16;                        // hidden columns per epilogue thread per 64-column chunk
+constexpr int kNP = 64 / kEW;                  // column parts -> kNP x 4 epilogue warps (latency hiding for the GELU math)
+constexpr int kEpiThreads = 128 * kNP;
+constexpr int kThreadsMlp = 192 + kEpiThreads;
 
 struct MlpTc {
   int B, Ci, Cip, H, Hp, NC, N2, Co2, S, fbufs, mode, act, b1_per_sample, dact, direct;
@@ -45,7 +48,7 @@ __host__ __device__ inline MlpLayout mlp_layout(const MlpTc& p) {
   L.b1 = o; o += (uint32_t)p.Hp * 4;
   L.w2v = o; o += (uint32_t)p.Hp * 4;
   L.dw2 = o; o += (uint32_t)p.Hp * 4;
-  L.part = o; o += 2 * 128 * 4;
+  L.part = o; o += 2 * (kNP - 1) * 128 * 4;
   o = (o + 1023u) & ~1023u;
   L.stages = o;
   L.stage_bytes = (uint32_t)p.Cip * 512;
@@ -113,10 +116,10 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
   if (tid == 0) {
     for (int s = 0; s < p.S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 128); }
     mbar_init(x_full, 128); mbar_init(x_empty, 1);
-    for (int a = 0; a < 4; a++) { mbar_init(&acc1_full[a], 1); mbar_init(&acc1_empty[a], 256); }
+    for (int a = 0; a < 4; a++) { mbar_init(&acc1_full[a], 1); mbar_init(&acc1_empty[a], kEpiThreads); }
     for (int a = 0; a < 2; a++) {
-      mbar_init(&f_full[a], 256); mbar_init(&f_empty[a], 1);
-      mbar_init(&acc2_full[a], 1); mbar_init(&acc2_empty[a], 256);
+      mbar_init(&f_full[a], kEpiThreads); mbar_init(&f_empty[a], 1);
+      mbar_init(&acc2_full[a], 1); mbar_init(&acc2_empty[a], kEpiThreads);
     }
     fence_barrier_init();
   }
@@ -243,8 +246,8 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
       mbar_arrive(x_full);
     }
   } else {
-    // ===================== epilogue: 8 warps = 4 lane quadrants x 2 column halves =====================
-    const int half = (warp - 6) >> 2;
+    // ===================== epilogue: 4 lane quadrants x kNP column parts =====================
+    const int part_id = (warp - 6) >> 2;
     const int quad = warp & 3;
     const int t = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
@@ -262,25 +265,25 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
       for (int c = 0; c < NC; c++) {
         const long n = n1 + c;
         const int ab = (int)(n % NA);
-        const int col0 = c * 64 + half * 32;   // first hidden index of this thread's 32 columns
+        const int col0 = c * 64 + part_id * kEW;   // first hidden index of this thread's kEW columns
         mbar_wait(&acc1_full[ab], (uint32_t)(n / NA) & 1u);
         tc_fence_after();
-        float v[32];
-        tmem_ld32(t_acc1 + lane_base + 64u * ab + half * 32, v);
+        float v[kEW];
+        tmem_ld16(t_acc1 + lane_base + 64u * ab + part_id * kEW, v);
         // hidden bias for this thread's 32 columns (loads overlap the TMEM read); pad columns (>= H) carry zero
         // W1 rows, zero w2 and a finite bias, so they contribute exactly 0 and need no branches
-        float bj[32];
+        float bj[kEW];
         if (b1g) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) bj[j] = __ldg(b1g + min(col0 + j, p.H - 1));
+          for (int j = 0; j < kEW; j++) bj[j] = __ldg(b1g + min(col0 + j, p.H - 1));
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(bj + j) = *reinterpret_cast<const float4*>(sb1 + col0 + j);
+          for (int j = 0; j < kEW; j += 4) *reinterpret_cast<float4*>(bj + j) = *reinterpret_cast<const float4*>(sb1 + col0 + j);
         }
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&acc1_empty[ab]);
-        float ga[32];
+        float ga[kEW];
         if (GELU) {
           // packed fp32x2 math: one FMA-pipe instruction per two hidden units
           float2* v2 = reinterpret_cast<float2*>(v);
@@ -289,7 +292,7 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
             float2* ga2 = reinterpret_cast<float2*>(ga);
             const float2 gv2 = b2no_f2(gv);
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
+            for (int j = 0; j < kEW / 2; j++) {
               const float2 w2p = *reinterpret_cast<const float2*>(sw2 + col0 + 2 * j);
               float2 val, grad;
               b2no_gelu2_both(__fadd2_rn(v2[j], b2[j]), &val, &grad);
@@ -298,17 +301,17 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
             }
           } else if (direct) {
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
+            for (int j = 0; j < kEW / 2; j++) {
               const float2 w2p = *reinterpret_cast<const float2*>(sw2 + col0 + 2 * j);
               oacc = __ffma2_rn(b2no_gelu2(__fadd2_rn(v2[j], b2[j])), w2p, oacc);
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; j++) v2[j] = b2no_gelu2(__fadd2_rn(v2[j], b2[j]));
+            for (int j = 0; j < kEW / 2; j++) v2[j] = b2no_gelu2(__fadd2_rn(v2[j], b2[j]));
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
+          for (int j = 0; j < kEW; j++) {
             const float z = v[j] + bj[j];
             if (bwd) {
               ga[j] = gv * b2no_act(z, p.act);
@@ -325,31 +328,44 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
           if (p.gz) {
             float* gp = p.gz + ((size_t)b * p.H + col0) * p.P + px;
 #pragma unroll
-            for (int j = 0; j < 32; j++)
+            for (int j = 0; j < kEW; j++)
               if (col0 + j < p.H) gp[(size_t)j * p.P] = v[j];
           }
-          // dw2[col0 + l] += sum over the warp's 32 pixels of g * act(z): transposing butterfly, lane l ends with column l
+          // dw2[col] += sum over the warp's 32 pixels of g * act(z): transposing butterfly; while a lane still holds
+          // more than one column the halves are exchanged, afterwards plain xor-sums.  Column kept by lane l:
+          // l >> (5 - log2 kEW); one lane of each group of 32 / kEW adds it to the shared-memory total.
+          {
+            int cnt = kEW;
 #pragma unroll
-          for (int s = 0; s < 5; s++) {
-            const int off = 16 >> s;
-            const int hw = 16 >> s;
-            const bool upper = (lane & off) != 0;
+            for (int s = 0; s < 5; s++) {
+              const int off = 16 >> s;
+              if (cnt > 1) {
+                const int hw = cnt >> 1;
+                const bool upper = (lane & off) != 0;
 #pragma unroll
-            for (int i = 0; i < hw; i++) {
-              const float a0 = ga[i], a1 = ga[i + hw];
-              const float send = upper ? a0 : a1;
-              const float keep = upper ? a1 : a0;
-              ga[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                for (int i = 0; i < kEW / 2; i++) {
+                  if (i < hw) {
+                    const float a0 = ga[i], a1 = ga[i + hw];
+                    const float send = upper ? a0 : a1;
+                    const float keep = upper ? a1 : a0;
+                    ga[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                  }
+                }
+                cnt = hw;
+              } else {
+                ga[0] += __shfl_xor_sync(0xffffffffu, ga[0], off);
+              }
             }
+            constexpr int kDup = 32 / kEW;
+            if ((lane & (kDup - 1)) == 0) atomicAdd(&sdw2[col0 + lane / kDup], ga[0]);
           }
-          atomicAdd(&sdw2[col0 + lane], ga[0]);
         }
         const int fb = (int)(n % p.fbufs);
         mbar_wait(&f_empty[fb], ((uint32_t)(n / p.fbufs) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t fa = t_f + lane_base + 128u * fb + half * 32;
+        const uint32_t fa = t_f + lane_base + 128u * fb + part_id * kEW;
 #pragma unroll
-        for (int j0 = 0; j0 < 32; j0 += 8) {
+        for (int j0 = 0; j0 < kEW; j0 += 8) {
           float lo[8];
 #pragma unroll
           for (int j = 0; j < 8; j++) lo[j] = tf32_lo(v[j0 + j]);
@@ -362,19 +378,24 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
       }
       n1 += NC;
       if (direct) {
-        // the two column halves of a pixel live in different warps: combine through shared memory (double buffered,
-        // one named barrier over the 256 epilogue threads per tile)
-        float* part = (float*)(smem + L.part) + (it & 1) * 128;
-        if (half == 1) part[t] = oacc.x + oacc.y;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (half == 0) p.out[(size_t)b * p.P + px] = (oacc.x + oacc.y) + part[t] + (p.b2 ? __ldg(p.b2) : 0.f);
+        // the column parts of a pixel live in different warps: combine through shared memory (double buffered, one
+        // named barrier over the epilogue threads per tile)
+        float* part = (float*)(smem + L.part) + (size_t)(it & 1) * (kNP - 1) * 128;
+        if (part_id > 0) part[(part_id - 1) * 128 + t] = oacc.x + oacc.y;
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        if (part_id == 0) {
+          float o = (oacc.x + oacc.y) + (p.b2 ? __ldg(p.b2) : 0.f);
+#pragma unroll
+          for (int q = 0; q < kNP - 1; q++) o += part[q * 128 + t];
+          p.out[(size_t)b * p.P + px] = o;
+        }
         continue;
       }
       // ---- epilogue-2 ----
       const int a2 = it & 1;
       mbar_wait(&acc2_full[a2], (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
-      for (int cb = half; cb * 16 < p.N2; cb += 2) {
+      for (int cb = part_id; cb * 16 < p.N2; cb += kNP) {
         float o[16];
         tmem_ld16(t_acc2 + lane_base + (uint32_t)(a2 * p.N2 + cb * 16), o);
         tmem_ld_wait();
