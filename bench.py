@@ -277,11 +277,10 @@ def run_b200(args):
             graphed = None
 
     def eager_step(p, t):
-        opt.zero_grad()
+        opt.zero_grad(set_to_none=True)
         loss = loss_fn(model(p, None), t)
         loss.backward()
-        if world > 1:
-            dist.all_reduce(opt.bucket.flat, op=dist.ReduceOp.SUM)
+        opt.sync_grads()
         opt.step(grad_scale=1.0 / world)
         return loss.detach()
 

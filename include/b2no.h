@@ -160,6 +160,12 @@ int b2no_rel_l2_sums(const float* x, const float* y, float* sums, int batch, int
 /* dx = coef[b] * (x - y)  with coef[b] precomputed by the host from sums (and the upstream gradient) */
 int b2no_rel_l2_bwd(const float* x, const float* y, const float* coef, float* dx, int batch,
                     int64_t n_per_sample, void* stream);
+/* Device-side tail of LpLoss.rel (utilities3.py:331-334): loss = sum_b (size_average: mean_b) of sqrt(sums[b][0]) /
+ * sqrt(sums[b][1]); coef[b] (optional) = scale / (||x_b - y_b|| ||y_b||), the factor of the backward. */
+int b2no_rel_l2_finish(const float* sums, float* loss, float* coef, int batch, int size_average, void* stream);
+/* dx = g[0] * coef[b] * (x - y): backward of LpLoss.rel with the upstream scalar gradient g read on the device */
+int b2no_rel_l2_bwd_g(const float* x, const float* y, const float* coef, const float* g, float* dx, int batch,
+                      int64_t n_per_sample, void* stream);
 
 /* ---- optimizer ---------------------------------------------------------------- */
 /* One fused Adam update over a flat fp32 buffer (complex parameters as their (re, im) view), torch.optim.Adam
@@ -168,6 +174,12 @@ int b2no_rel_l2_bwd(const float* x, const float* y, const float* coef, float* dx
  * step_counter is a DEVICE int incremented by the call, so a captured CUDA graph replays correctly. */
 int b2no_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int* step_counter,
                    float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream);
+/* flat[offsets[s] .. offsets[s+1]) = src_ptrs[s][0 .. counts[s]) (zero fill beyond counts[s] or when src_ptrs[s] is
+ * null): the per-parameter gradients autograd produced, gathered into the flat bucket the all-reduce and
+ * b2no_adam_step work on.  src_ptrs (nseg device pointers), offsets (nseg + 1) and counts (nseg) are DEVICE arrays.
+ * Replaces the per-parameter `p.grad += g` of run_pde_observers.py:192 (loss.backward()). */
+int b2no_gather_segments(float* flat, const void* src_ptrs, const int64_t* offsets, const int64_t* counts, int nseg,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -98,6 +98,9 @@ def lib():
     L.b2no_rno_gate_bwd.argtypes = [vp] * 9 + [i64, vp]
     L.b2no_rel_l2_sums.argtypes = [vp, vp, vp, i32, i64, vp]
     L.b2no_rel_l2_bwd.argtypes = [vp, vp, vp, vp, i32, i64, vp]
+    L.b2no_rel_l2_finish.argtypes = [vp, vp, vp, i32, i32, vp]
+    L.b2no_rel_l2_bwd_g.argtypes = [vp, vp, vp, vp, vp, i32, i64, vp]
+    L.b2no_gather_segments.argtypes = [vp, vp, vp, vp, i32, vp]
     f32 = C.c_float
     L.b2no_adam_step.argtypes = [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, f32, vp]
     for name in EXPORTS:
@@ -113,7 +116,7 @@ EXPORTS = [
     "b2no_dft_forward", "b2no_dft_inverse", "b2no_mix", "b2no_mix_dw",
     "b2no_act_bwd", "b2no_pw_wgrad_scratch_floats", "b2no_pw_wgrad", "b2no_mlp_head_fwd", "b2no_mlp_head_bwd_scratch_floats", "b2no_mlp_head_bwd_supported", "b2no_mlp_head_bwd",
     "b2no_rno_gate_fwd", "b2no_rno_gate_bwd", "b2no_rel_l2_sums", "b2no_rel_l2_bwd",
-    "b2no_adam_step",
+    "b2no_rel_l2_finish", "b2no_rel_l2_bwd_g", "b2no_adam_step", "b2no_gather_segments",
 ]
 
 

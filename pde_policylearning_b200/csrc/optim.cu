@@ -61,3 +61,30 @@ extern "C" int b2no_adam_step(float* param, const float* grad, float* exp_avg, f
   B2NO_LAUNCH_CHECK();
   return 0;
 }
+
+// Gathers per-parameter gradient tensors into the flat bucket: flat[offsets[s] .. offsets[s+1]) = src[s][0 ..) (a null
+// src[s], or the part of a slot beyond counts[s], is zero-filled).  Replaces one torch accumulate kernel per parameter
+// (autograd's `p.grad += g`) by ONE launch; the pointer table is constant inside a captured CUDA graph.
+__global__ void __launch_bounds__(256)
+k_gather_segments(float* __restrict__ flat, const float* const* __restrict__ src, const long long* __restrict__ offsets,
+                  const long long* __restrict__ counts, int nseg) {
+  for (int s = blockIdx.y; s < nseg; s += gridDim.y) {
+    const long long o0 = offsets[s], n = offsets[s + 1] - o0, cnt = counts[s];
+    const float* sp = src[s];
+    float* dp = flat + o0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+      dp[i] = (sp && i < cnt) ? sp[i] : 0.f;
+  }
+}
+
+extern "C" int b2no_gather_segments(float* flat, const void* src_ptrs, const int64_t* offsets, const int64_t* counts,
+                                    int nseg, void* stream) {
+  if (!flat || !src_ptrs || !offsets || !counts || nseg < 0) return B2NO_E_ARG;
+  if (nseg == 0) return 0;
+  dim3 grid(32, (unsigned)(nseg < 1024 ? nseg : 1024));
+  k_gather_segments<<<grid, 256, 0, (cudaStream_t)stream>>>(flat, (const float* const*)src_ptrs, (const long long*)offsets,
+                                                           (const long long*)counts, nseg);
+  B2NO_LAUNCH_CHECK();
+  return 0;
+}

@@ -464,3 +464,57 @@ extern "C" int b2no_rel_l2_bwd(const float* x, const float* y, const float* coef
   B2NO_LAUNCH_CHECK();
   return 0;
 }
+
+// loss = sum_b (or mean_b) sqrt(sums[b][0]) / sqrt(sums[b][1]);  coef[b] = scale / (||x_b - y_b|| * ||y_b||) is what the
+// backward multiplies (x - y) with (scale = 1/B for the mean).  One block; fixed summation order (deterministic).
+__global__ void __launch_bounds__(256)
+k_rel_l2_finish(const float* __restrict__ sums, float* __restrict__ loss, float* __restrict__ coef, int batch, float scale) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < batch; b += 256) {
+    const float d = sqrtf(sums[2 * b]), n = sqrtf(sums[2 * b + 1]);
+    acc += d / n;
+    if (coef) coef[b] = scale / (d * n);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) s += red[w];
+    *loss = s * scale;
+  }
+}
+
+extern "C" int b2no_rel_l2_finish(const float* sums, float* loss, float* coef, int batch, int size_average, void* stream) {
+  if (!sums || !loss || batch < 1) return B2NO_E_ARG;
+  k_rel_l2_finish<<<1, 256, 0, (cudaStream_t)stream>>>(sums, loss, coef, batch, size_average ? 1.0f / (float)batch : 1.0f);
+  B2NO_LAUNCH_CHECK();
+  return 0;
+}
+
+// dx = g * coef[b] * (x - y), g = the upstream scalar gradient read on the device
+__global__ void __launch_bounds__(256)
+k_rel_l2_bwd_g(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ coef,
+               const float* __restrict__ g, float* __restrict__ dx, long n) {
+  const int b = blockIdx.y;
+  const float c = __ldg(coef + b) * __ldg(g);
+  const size_t base = (size_t)b * n;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dx[base + i] = c * (x[base + i] - y[base + i]);
+}
+
+extern "C" int b2no_rel_l2_bwd_g(const float* x, const float* y, const float* coef, const float* g, float* dx, int batch,
+                                 int64_t n, void* stream) {
+  if (!x || !y || !coef || !g || !dx || batch < 1 || n < 1) return B2NO_E_ARG;
+  if (batch > 65535) return B2NO_E_UNSUPPORTED;
+  long bx = (n + 256 * 4 - 1) / (256 * 4);
+  if (bx < 1) bx = 1;
+  if (bx > 128) bx = 128;
+  dim3 grid((unsigned)bx, (unsigned)batch);
+  k_rel_l2_bwd_g<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, coef, g, dx, n);
+  B2NO_LAUNCH_CHECK();
+  return 0;
+}

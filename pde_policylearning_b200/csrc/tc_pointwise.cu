@@ -18,13 +18,15 @@
 //   - B operands (1x1 weights, A' rows) stay in shared memory, K-major no-swizzle core-matrix layout.
 // fp32 parity: every product is issued three times (3xTF32: hi*hi + lo*hi + hi*lo), error 4e-7 (tools/tc_probe.cu).
 //
-// Warp roles (448 threads, persistent CTAs, each CTA owns a contiguous run of tiles):
+// Warp roles (704 threads, persistent CTAs, each CTA owns a contiguous run of tiles):
 //   warp 0      TMA producer (X boxes, cp.async.bulk for the A' rows), S-deep mbarrier ring
 //   warp 1      MMA issuer (one lane): tcgen05.mma.kind::tf32 TS form, tcgen05.commit -> mbarriers
 //   warps 2-5   converter: shared memory -> TMEM A operand (double buffered)
-//   warps 6-13  epilogue: all eight warps work on each tile (4 lane quadrants x 2 column halves),
-//               tcgen05.ld -> bias/act -> coalesced global stores (a warp writes 128 B per output channel);
-//               two TMEM accumulators so the MMAs of tile i+1 overlap the epilogue of tile i
+//   warps 6-21  epilogue: all sixteen warps work on each tile (4 lane quadrants x 4 column parts of 8 channels: the
+//               epilogue is a latency chain -- tcgen05.ld, GELU, 128-byte stores per channel row -- and eight warps
+//               left the issue slots half empty), tcgen05.ld -> bias/act -> coalesced global stores;
+//               two TMEM accumulators so the MMAs of tile i+1 overlap the epilogue of tile i.  MODE 3 fetches the
+//               saved pre-activations of the NEXT tile before it waits for the current accumulator.
 #include <stdlib.h>
 #include <string.h>
 
@@ -35,10 +37,14 @@ using namespace tc;
 
 namespace {
 
-constexpr int kThreads = 448;
+constexpr int kParts = 4;                       // column parts of the epilogue (kParts x 4 warps)
+constexpr int kCW = 8;                          // output channels per epilogue thread per pass
+constexpr int kEpiThreadsPw = 128 * kParts;
+constexpr int kThreads = 192 + kEpiThreadsPw;
 
 struct PwTc {
   int B, Co, Np, C1, C1p, C2, C2p, Ks, Qp, R, S;
+  int Cz;             // > 0: MODE 3 streams the saved pre-activations dz through the TMA ring, [Cz x 128 px] per stage
   int tiles_per_img;
   long tiles, tiles_per_cta, P;
   const float* w1; int w1_t;
@@ -51,7 +57,7 @@ struct PwTc {
 };
 
 struct PwLayout {
-  uint32_t w1h, w1l, w2h, w2l, bias, stages, stage_bytes, x2, ah, al, bars, total;
+  uint32_t w1h, w1l, w2h, w2l, bias, stages, stage_bytes, x2, ah, al, dz, bars, total;
 };
 
 __host__ __device__ inline PwLayout pw_layout(const PwTc& p) {
@@ -65,7 +71,8 @@ __host__ __device__ inline PwLayout pw_layout(const PwTc& p) {
   o = (o + 1023u) & ~1023u;
   L.stages = o;
   L.x2 = xb1; L.ah = xb1 + xb2; L.al = L.ah + ab;
-  L.stage_bytes = (L.al + ab + 1023u) & ~1023u;
+  L.dz = (L.al + ab + 127u) & ~127u;
+  L.stage_bytes = (L.dz + (uint32_t)p.Cz * 512 + 1023u) & ~1023u;
   o += L.stage_bytes * p.S;
   L.bars = o;
   o += 8 * (2 * p.S + 8) + 16;
@@ -90,7 +97,8 @@ __device__ __forceinline__ float epi_value(float z, float mulv, float dzv, int a
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
-k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2, const PwTc p) {
+k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2, const __grid_constant__ CUtensorMap tm3,
+        const PwTc p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const PwLayout L = pw_layout(p);
@@ -125,16 +133,17 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
   }
   for (int i = tid; i < p.Np; i += kThreads) ((float*)(smem + L.bias))[i] = (p.bias && i < p.Co) ? p.bias[i] : 0.f;
   if (tid == 0) {
-    for (int s = 0; s < p.S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    // a stage is free when its MMAs have completed and (dz ring) every epilogue thread has taken its dz values
+    for (int s = 0; s < p.S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1 + ((MODE == 3 && p.Cz) ? kEpiThreadsPw : 0)); }
     for (int a = 0; a < 2; a++) {
       mbar_init(&a_full[a], 128); mbar_init(&a_empty[a], 1);
-      mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 256);
+      mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], kEpiThreadsPw);
     }
     fence_barrier_init();
   }
   fence_proxy_async();
   if (warp == 1) tmem_alloc(tslot, ncols);
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm1); if (p.C2p) tma_prefetch_desc(&tm2); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm1); if (p.C2p) tma_prefetch_desc(&tm2); if (MODE == 3 && p.Cz) tma_prefetch_desc(&tm3); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -150,7 +159,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const uint32_t bytes = xb1 + xb2 + 2 * ab;
+      const uint32_t bytes = xb1 + xb2 + 2 * ab + ((MODE == 3) ? (uint32_t)p.Cz * 512 : 0u);
       int it = 0;
       for (long tile = t_first; tile < t_end; tile++, it++) {
         const int s = it % p.S;
@@ -162,6 +171,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
         const int t_in_img = (int)(tile - (long)b * p.tiles_per_img);
         tma_load_3d(st, &tm1, &full[s], t_in_img * 128, 0, b);
         if (p.C2p) tma_load_3d(st + L.x2, &tm2, &full[s], t_in_img * 128, 0, b);
+        if (MODE == 3 && p.Cz) tma_load_3d(st + L.dz, &tm3, &full[s], t_in_img * 128, 0, b);
         if (p.Ks) {
           const size_t off = (size_t)tile * p.R * p.Qp * p.Np;
           bulk_load(st + L.ah, p.ahi + off, ab, &full[s]);
@@ -288,13 +298,19 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
       mbar_arrive(&a_full[a]);
     }
   } else {
-    // ===================== epilogue: 8 warps per tile = 4 lane quadrants x 2 column halves =====================
-    const int half = (warp - 6) >> 2;
+    // ===================== epilogue: 16 warps per tile = 4 lane quadrants x 4 column parts =====================
+    const int part = (warp - 6) >> 2;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int t = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const float* sbias = (const float*)(smem + L.bias);
     const bool nostore = (p.debug & 1) != 0;
+    // MODE 3: the saved pre-activations of the layer below arrive through the TMA ring (dz tile [Cz x 128 px] in the
+    // stage, S tiles ahead of their use); with one pass per tile (Co <= 32) the thread takes its 8 values and releases the
+    // stage right away, otherwise it reads them pass by pass and releases the stage at the end of the tile.  (Fetching
+    // them with plain loads left only one tile of dz in flight per SM: 133 us, 3.0 TB/s.)
+    const bool dz_ring = MODE == 3 && p.Cz > 0;
+    const bool dz_single = p.Co <= kCW * kParts;
     int it = 0;
     for (long tile = t_first; tile < t_end; tile++, it++) {
       const int a = it & 1;
@@ -302,23 +318,26 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
       const int b = (int)(tile / p.tiles_per_img);
       const long px = (tile - (long)b * p.tiles_per_img) * 128 + t;
       const size_t base = (size_t)b * p.Co * p.P + px;
-      // MODE 3: the saved pre-activations of the layer below are fetched BEFORE waiting for the accumulator, so the
-      // global-load latency overlaps the MMAs of this tile instead of following them
-      float dvn[16];
-      if (MODE == 3) {
+      const int s = it % p.S;
+      const float* sdz = (const float*)(smem + L.stages + (size_t)s * L.stage_bytes + L.dz);
+      float dcur[kCW];
+      if (dz_ring) {
+        mbar_wait(&full[s], (uint32_t)(it / p.S) & 1u);
+        if (dz_single) {
 #pragma unroll
-        for (int j = 0; j < 16; j++)
-          dvn[j] = (half * 16 + j < p.Co) ? __ldg(p.dz + base + (size_t)(half * 16 + j) * p.P) : 0.f;
+          for (int j = 0; j < kCW; j++) dcur[j] = (part * kCW + j < p.Cz) ? sdz[(part * kCW + j) * 128 + t] : 0.f;
+          mbar_arrive(&empty[s]);
+        }
       }
       mbar_wait(&acc_full[a], aph);
       tc_fence_after();
-      for (int c0 = half * 16; c0 < p.Co; c0 += 32) {
-        float v[16];
-        tmem_ld16(tbase + lane_base + (uint32_t)(a * p.Np + c0), v);
+      for (int c0 = part * kCW; c0 < p.Co; c0 += kCW * kParts) {
+        float v[kCW];
+        tmem_ld8(tbase + lane_base + (uint32_t)(a * p.Np + c0), v);
         if (MODE == 0) {
-          float av[16], mv[16], dv[16];
+          float av[kCW], mv[kCW], dv[kCW];
 #pragma unroll
-          for (int j = 0; j < 16; j++) {
+          for (int j = 0; j < kCW; j++) {
             const bool ok = c0 + j < p.Co;
             const size_t idx = base + (size_t)(c0 + j) * p.P;
             av[j] = (p.add && ok) ? __ldg(p.add + idx) : 0.f;
@@ -327,7 +346,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
           }
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; j++) {
+          for (int j = 0; j < kCW; j++) {
             if (c0 + j < p.Co) {
               const size_t idx = base + (size_t)(c0 + j) * p.P;
               const float z = v[j] + sbias[c0 + j] + av[j];
@@ -337,44 +356,59 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
             }
           }
         } else {
-          float dv[16];
+          float dv[kCW];
           if (MODE == 3) {
-            if (c0 == half * 16) {
+            if (dz_ring && dz_single) {
 #pragma unroll
-              for (int j = 0; j < 16; j++) dv[j] = dvn[j];
+              for (int j = 0; j < kCW; j++) dv[j] = dcur[j];
+            } else if (dz_ring) {
+#pragma unroll
+              for (int j = 0; j < kCW; j++) dv[j] = (c0 + j < p.Cz) ? sdz[(c0 + j) * 128 + t] : 0.f;
             } else {
 #pragma unroll
-              for (int j = 0; j < 16; j++) dv[j] = (c0 + j < p.Co) ? __ldg(p.dz + base + (size_t)(c0 + j) * p.P) : 0.f;
+              for (int j = 0; j < kCW; j++) dv[j] = (c0 + j < p.Co) ? __ldg(p.dz + base + (size_t)(c0 + j) * p.P) : 0.f;
             }
             // packed GELU' (two channels per FMA-pipe instruction)
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
+            for (int j = 0; j < kCW; j += 2) {
               const float2 gg = b2no_gelu2_grad(make_float2(dv[j], dv[j + 1]));
               dv[j] = gg.x; dv[j + 1] = gg.y;
             }
           }
-          float bv[16];
+          float bv[kCW];
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(bv + j) = *reinterpret_cast<const float4*>(sbias + c0 + j);
+          for (int j = 0; j < kCW; j += 4) *reinterpret_cast<float4*>(bv + j) = *reinterpret_cast<const float4*>(sbias + c0 + j);
           tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < kCW; j++) v[j] += bv[j];
           float* yp = p.y + base + (size_t)c0 * p.P;
-          if (MODE == 2 && p.preact) {
-            float* zp = p.preact + base + (size_t)c0 * p.P;
+          if (MODE == 2) {
+            if (p.preact) {
+              float* zp = p.preact + base + (size_t)c0 * p.P;
 #pragma unroll
-            for (int j = 0; j < 16; j++)
-              if (c0 + j < p.Co) zp[(size_t)j * p.P] = v[j] + bv[j];
-          }
-#pragma unroll
-          for (int j = 0; j < 16; j++) {
-            if (c0 + j < p.Co) {
-              const float r = epi_value<MODE>(v[j] + bv[j], 1.f, MODE == 3 ? dv[j] : 0.f, 0, 0);
-              if (!nostore) yp[(size_t)j * p.P] = r;
+              for (int j = 0; j < kCW; j++)
+                if (c0 + j < p.Co) zp[(size_t)j * p.P] = v[j];
             }
+            // packed GELU (two channels per FMA-pipe instruction)
+#pragma unroll
+            for (int j = 0; j < kCW; j += 2) {
+              const float2 gg = b2no_gelu2(make_float2(v[j], v[j + 1]));
+              v[j] = gg.x; v[j + 1] = gg.y;
+            }
+          } else if (MODE == 3) {
+#pragma unroll
+            for (int j = 0; j < kCW; j++) v[j] *= dv[j];
+          }
+          if (!nostore) {
+#pragma unroll
+            for (int j = 0; j < kCW; j++)
+              if (c0 + j < p.Co) yp[(size_t)j * p.P] = v[j];
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[a]);
+      if (dz_ring && !dz_single) mbar_arrive(&empty[s]);
     }
   }
   tc_fence_before();
@@ -498,6 +532,12 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
     p.alo = work + afl;
   }
   if (pw_tmem_cols(p) > 512) return 1;
+  const bool extras = p.add || p.mul;
+  int mode = 0;
+  if (!extras && !p.dact && p.act == B2NO_ACT_NONE && !p.preact) mode = 1;
+  else if (!extras && !p.dact && p.act == B2NO_ACT_GELU) mode = 2;
+  else if (!extras && p.dact == B2NO_ACT_GELU && p.act == B2NO_ACT_NONE && !p.preact) mode = 3;
+  if (mode == 3 && (((uintptr_t)p.dz & 15) == 0) && channels <= 256) p.Cz = b2no_round_up(channels, 8);
   // shared-memory budget -> number of stages
   int dev = 0, max_smem = 0;
   B2NO_CHECK_CUDA(cudaGetDevice(&dev));
@@ -507,9 +547,16 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
     L = pw_layout(p);
     if ((int)L.total <= max_smem) break;
   }
+  if (p.S < 3 && p.Cz) {          // not enough room for a useful ring with the dz tile: plain loads instead
+    p.Cz = 0;
+    for (p.S = 6; p.S >= 2; p.S--) {
+      L = pw_layout(p);
+      if ((int)L.total <= max_smem) break;
+    }
+  }
   if (p.S < 2) return 1;
 
-  CUtensorMap tm1, tm2;
+  CUtensorMap tm1, tm2, tm3;
   {
     uint64_t dims[3] = {(uint64_t)pixels, (uint64_t)p.C1, (uint64_t)batch};
     uint64_t str[3] = {4, (uint64_t)pixels * 4, (uint64_t)pixels * 4 * p.C1};
@@ -521,6 +568,13 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
       uint64_t str2[3] = {4, (uint64_t)pixels * 4, (uint64_t)pixels * 4 * p.C2};
       uint32_t box2[3] = {128, (uint32_t)p.C2p, 1};
       if (make_tmap_f32(&tm2, e->pw2_x, 3, dims2, str2, box2, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+    }
+    tm3 = tm1;
+    if (p.Cz) {
+      uint64_t dims3[3] = {(uint64_t)pixels, (uint64_t)channels, (uint64_t)batch};
+      uint64_t str3[3] = {4, (uint64_t)pixels * 4, (uint64_t)pixels * 4 * channels};
+      uint32_t box3[3] = {128, (uint32_t)p.Cz, 1};
+      if (make_tmap_f32(&tm3, p.dz, 3, dims3, str3, box3, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
     }
   }
   if (spec) {
@@ -545,11 +599,6 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
 #undef INVH_LAUNCH
     B2NO_LAUNCH_CHECK();
   }
-  const bool extras = p.add || p.mul;
-  int mode = 0;
-  if (!extras && !p.dact && p.act == B2NO_ACT_NONE && !p.preact) mode = 1;
-  else if (!extras && !p.dact && p.act == B2NO_ACT_GELU) mode = 2;
-  else if (!extras && p.dact == B2NO_ACT_GELU && p.act == B2NO_ACT_NONE && !p.preact) mode = 3;
   long grid = p.tiles < b2no_sm_count() ? p.tiles : b2no_sm_count();
   p.tiles_per_cta = (p.tiles + grid - 1) / grid;
   grid = (p.tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
@@ -560,7 +609,7 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
 #define LAUNCH(M)                                                                                                  \
   do {                                                                                                             \
     B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_pw_tc<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));  \
-    k_pw_tc<M><<<(unsigned)grid, kThreads, L.total, st>>>(tm1, tm2, p);                                           \
+    k_pw_tc<M><<<(unsigned)grid, kThreads, L.total, st>>>(tm1, tm2, tm3, p);                                           \
   } while (0)
   switch (mode) {
     case 1: LAUNCH(1); break;

@@ -6,11 +6,14 @@
 //   A = G tile (M = output channels).  Few channels (32) would waste 3/4 of a 128-row shared-memory A read per MMA
 //       (measured: the SS form was shared-memory bound, 1.8 TB/s), so the converter warps (thread = channel row) move
 //       the G tile into TMEM as hi (raw fp32) | lo = rna_tf32(g - trunc g) and the MMAs run in the TS form;
-//   B = X tile straight from the TMA box plus a constant block of ones rows (so the same MMAs also produce db) and an
-//       elementwise lo copy made in shared memory by the converter warps;
-//   D = [Co x (Ci + 16)] fp32 in TMEM, accumulated over every tile a CTA owns and written once at the end as a per-CTA
-//       partial; k_pw_wgrad_reduce (pointwise.cu) sums the partials deterministically.
+//   B = X tile straight from the TMA box; its elementwise lo copy lives in a separate two-slot ring (one slot per A-ring
+//       slot) written by the converter warps, so a TMA stage holds nothing but the 2 x TP x channels payload;
+//   D = [Co x Ci] fp32 in TMEM, accumulated over every tile a CTA owns and written once at the end as a per-CTA
+//       partial; k_pw_wgrad_reduce (pointwise.cu) sums the partials deterministically;
+//   db[o] = sum G[o, .] is summed in registers by the converter thread that owns row o (it reads every G element anyway).
 // 3xTF32: hi*hi + lo*hi + hi*lo.
+// HBM-bound: what matters is bytes in flight per SM.  With the lo copy and a ones block inside every stage only 3 stages
+// (96 KB of payload) fitted and the bare TMA ring topped out at 4.6 TB/s; payload-only stages give 6 x 32 KB.
 #include <stdlib.h>
 #include <string.h>
 
@@ -31,21 +34,24 @@ struct WgTc {
   int debug;    // ablation (B2NO_WG_DEBUG): 1 no X-lo pass, 2 no G conversion, 4 no MMAs
 };
 
-struct WgLayout { uint32_t gbytes, xbytes, x, xlo, stage_bytes, bars, total; };
+struct WgLayout { uint32_t gbytes, xbytes, x, stage_bytes, lo, lo_bytes, dbs, bars, total; };
 
 __host__ __device__ inline WgLayout wg_layout(const WgTc& p) {
   WgLayout L;
   L.gbytes = (uint32_t)p.Cop * p.TP * 4;
-  L.xbytes = (uint32_t)(p.Cip + 16) * p.TP * 4;
-  L.x = L.gbytes; L.xlo = L.x + L.xbytes;
-  L.stage_bytes = (L.gbytes + 2 * L.xbytes + 1023u) & ~1023u;
-  L.bars = L.stage_bytes * p.S;
+  L.xbytes = (uint32_t)p.Cip * p.TP * 4;
+  L.x = L.gbytes;
+  L.stage_bytes = (L.gbytes + L.xbytes + 1023u) & ~1023u;
+  L.lo = L.stage_bytes * p.S;
+  L.lo_bytes = ((uint32_t)p.Cip * p.SUB * 4 + 1023u) & ~1023u;     // one slot = the X boxes of one MMA chunk
+  L.dbs = L.lo + 2 * L.lo_bytes;
+  L.bars = L.dbs + 2u * p.mblocks * 128 * 4;
   L.total = L.bars + 8 * (2 * p.S + 5) + 16 + 1024;
   return L;
 }
 
-// TMEM columns: A operand ring [buf 0/1][M-block][hi TP | lo TP], then the accumulators [M-block][Cip + 16]
-__host__ __device__ inline uint32_t wg_tmem_cols(const WgTc& p) { return 4u * p.SUB * p.mblocks + (uint32_t)p.mblocks * (p.Cip + 16); }
+// TMEM columns: A operand ring [buf 0/1][M-block][hi SUB | lo SUB], then the accumulators [M-block][Cip]
+__host__ __device__ inline uint32_t wg_tmem_cols(const WgTc& p) { return 4u * p.SUB * p.mblocks + (uint32_t)p.mblocks * p.Cip; }
 
 __global__ void __launch_bounds__(kThreadsWg, 1)
 k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUtensorMap tmx, const WgTc p) {
@@ -59,20 +65,10 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
   uint64_t* done = a_empty + 2;
   uint32_t* tslot = (uint32_t*)(done + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int NW = p.Cip + 16, TP = p.TP;
+  const int NW = p.Cip, TP = p.TP;
   uint32_t ncols = 32;
   while (ncols < wg_tmem_cols(p)) ncols <<= 1;
 
-  // zero the X regions once (channel pad rows, ones blocks), then write the ones rows: row Cip of every X box, hi copy only
-  for (int s = 0; s < p.S; s++)
-    for (uint32_t i = tid; i < 2 * L.xbytes / 16; i += kThreadsWg)
-      ((float4*)(smem + (size_t)s * L.stage_bytes + L.x))[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncthreads();
-  for (int i = tid; i < p.S * p.nb * 32; i += kThreadsWg) {
-    const int s = i / (p.nb * 32), r = i - s * (p.nb * 32);
-    const int j = r >> 5, e = r & 31;
-    ((float*)(smem + (size_t)s * L.stage_bytes + L.x + (size_t)j * NW * 128 + (size_t)p.Cip * 128))[e] = 1.0f;
-  }
   if (tid == 0) {
     for (int s = 0; s < p.S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; a++) { mbar_init(&a_full[a], 128); mbar_init(&a_empty[a], 1); }
@@ -133,9 +129,9 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
             uint32_t a2 = acc;
             for (int pass = 0; pass < 3; pass++) {
               const uint32_t ga = pass == 1 ? a0 + SUB : a0;
-              const uint32_t xa = st + (pass == 2 ? L.xlo : L.x);
+              const uint32_t xa = pass == 2 ? sbase + L.lo + (uint32_t)ab * L.lo_bytes : st + L.x + (uint32_t)(sub * nbs) * NW * 128;
               for (int j = 0; j < nbs; j++) {
-                const uint64_t dx = smem_desc(xa + (uint32_t)(sub * nbs + j) * NW * 128, 16, 1024, LAYOUT_SW128);
+                const uint64_t dx = smem_desc(xa + (uint32_t)j * NW * 128, 16, 1024, LAYOUT_SW128);
 #pragma unroll
                 for (int ks = 0; ks < 4; ks++) {
                   mma_tf32_ts(d, ga + (uint32_t)(j * 32 + ks * 8), dx + (uint64_t)(ks * 2), idesc, a2);
@@ -162,6 +158,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
     const int quad = warp & 3;
     const int m = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    float dbsum[3] = {0.f, 0.f, 0.f};          // db partial of rows m, 128 + m, 256 + m over this group's chunks
     int it = 0;
     long n = 0;
     for (long tile = t_first; tile < t_end; tile++, it++) {
@@ -172,36 +169,54 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
       for (int sub = 0; sub < nsub; sub++, n++) {
         const int ab = (int)(n & 1);
         if (ab != grp) continue;
+        mbar_wait(&a_empty[ab], ((uint32_t)(n >> 1) & 1u) ^ 1u);     // MMAs of this slot's previous chunk are complete
+        tc_fence_after();
         {
-          // lo copy of this sub-chunk's X boxes, elementwise (layout-agnostic); the ones rows give lo = 0
-          const uint32_t off = (uint32_t)(sub * nbs) * NW * 128, cnt = (uint32_t)nbs * NW * 128 / 16;
-          const float4* src = (const float4*)(st + L.x + off);
-          float4* dst = (float4*)(st + L.xlo + off);
+          // lo copy of this chunk's X boxes into the slot's lo buffer, elementwise (layout-agnostic)
+          const uint32_t cnt = (uint32_t)nbs * NW * 128 / 16;
+          const float4* src = (const float4*)(st + L.x + (size_t)(sub * nbs) * NW * 128);
+          float4* dst = (float4*)(smem + L.lo + (size_t)ab * L.lo_bytes);
           for (uint32_t i = ct; i < ((p.debug & 1) ? 0u : cnt); i += 128) {
             const float4 x = src[i];
             dst[i] = make_float4(x.x - tf32_trunc(x.x), x.y - tf32_trunc(x.y), x.z - tf32_trunc(x.z), x.w - tf32_trunc(x.w));
           }
         }
-        mbar_wait(&a_empty[ab], ((uint32_t)(n >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        for (int mb = 0; mb < ((p.debug & 2) ? 0 : p.mblocks); mb++) {
+#pragma unroll
+        for (int mb = 0; mb < 3; mb++) {
+          if (mb >= ((p.debug & 2) ? 0 : p.mblocks)) break;
           const int row = mb * 128 + m;
           const uint32_t a0 = tbase + lane_base + (uint32_t)((ab * p.mblocks + mb) * 2 * SUB);
-          for (int j = 0; j < nbs; j++) {
-            float hi[32], lo[32];
-            if (row < p.Cop) {
-              const uint8_t* rp = st + (size_t)(sub * nbs + j) * p.Cop * 128 + (size_t)row * 128;
+          // tcgen05.st is warp-collective (.sync.aligned): the branch must be warp-uniform, so a warp that owns at least
+          // one real row converts all 32 of its rows (pad rows as zeros); warps of pure pad rows zero their lanes once
+          if (mb * 128 + quad * 32 < p.Cop) {
+            const bool real = row < p.Cop;
+            for (int j = 0; j < nbs; j++) {
+              float hi[32], lo[32];
+              const uint8_t* rp = st + (size_t)(sub * nbs + j) * p.Cop * 128 + (size_t)(real ? row : 0) * 128;
 #pragma unroll
               for (int i = 0; i < 8; i++)
                 *reinterpret_cast<float4*>(hi + 4 * i) = *reinterpret_cast<const float4*>(rp + ((i ^ (row & 7)) << 4));
+              if (!real) {
+#pragma unroll
+                for (int i = 0; i < 32; i++) hi[i] = 0.f;
+              }
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                s0 += hi[i]; s1 += hi[i + 1]; s2 += hi[i + 2]; s3 += hi[i + 3];
+              }
+              dbsum[mb] += (s0 + s1) + (s2 + s3);
 #pragma unroll
               for (int i = 0; i < 32; i++) lo[i] = hi[i] - tf32_trunc(hi[i]);   // exact; the tensor core truncates it to tf32
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; i++) { hi[i] = 0.f; lo[i] = 0.f; }
+              tmem_st16(a0 + (uint32_t)(j * 32), hi); tmem_st16(a0 + (uint32_t)(j * 32 + 16), hi + 16);
+              tmem_st16(a0 + (uint32_t)(SUB + j * 32), lo); tmem_st16(a0 + (uint32_t)(SUB + j * 32 + 16), lo + 16);
             }
-            tmem_st16(a0 + (uint32_t)(j * 32), hi); tmem_st16(a0 + (uint32_t)(j * 32 + 16), hi + 16);
-            tmem_st16(a0 + (uint32_t)(SUB + j * 32), lo); tmem_st16(a0 + (uint32_t)(SUB + j * 32 + 16), lo + 16);
+          } else if (n < 2) {
+            // pad rows (>= Cop) of an M block: zeroed once per ring slot, never written again
+            float z[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) z[i] = 0.f;
+            for (int c = 0; c < 2 * SUB; c += 16) tmem_st16(a0 + (uint32_t)c, z);
           }
         }
         tmem_st_wait();
@@ -210,29 +225,34 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
         mbar_arrive(&a_full[ab]);
       }
     }
+    // db: both groups publish their row sums, group A combines them (fixed order)
+    float* dbs = (float*)(smem + L.dbs);
+#pragma unroll
+    for (int mb = 0; mb < 3; mb++)
+      if (mb < p.mblocks) dbs[(grp * p.mblocks + mb) * 128 + m] = dbsum[mb];
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     // read-out (group A): thread = accumulator row
     if (grp == 0) {
-    mbar_wait(done, 0);
-    tc_fence_after();
-    float* pout = p.partial + (size_t)blockIdx.x * ((size_t)p.Co * p.Ci + p.Co);
-    const bool any = t_end > t_first;
-    for (int mb = 0; mb < p.mblocks; mb++) {
-      const int o = mb * 128 + m;
-      for (int c0 = 0; c0 < NW; c0 += 16) {
-        float v[16];
-        tmem_ld16(t_acc + lane_base + (uint32_t)(mb * NW + c0), v);
-        tmem_ld_wait();
-        if (o < p.Co) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+      float* pout = p.partial + (size_t)blockIdx.x * ((size_t)p.Co * p.Ci + p.Co);
+      const bool any = t_end > t_first;
+      for (int mb = 0; mb < p.mblocks; mb++) {
+        const int o = mb * 128 + m;
+        for (int c0 = 0; c0 < NW; c0 += 16) {
+          float v[16];
+          tmem_ld16(t_acc + lane_base + (uint32_t)(mb * NW + c0), v);
+          tmem_ld_wait();
+          if (o < p.Co) {
 #pragma unroll
-          for (int j = 0; j < 16; j++) {
-            const int c = c0 + j;
-            const float val = any ? v[j] : 0.f;
-            if (c < p.Ci) pout[(size_t)o * p.Ci + c] = val;
-            else if (c == p.Cip) pout[(size_t)p.Co * p.Ci + o] = val;
+            for (int j = 0; j < 16; j++) {
+              const int c = c0 + j;
+              if (c < p.Ci) pout[(size_t)o * p.Ci + c] = any ? v[j] : 0.f;
+            }
           }
         }
+        if (o < p.Co) pout[(size_t)p.Co * p.Ci + o] = dbs[mb * 128 + m] + dbs[(p.mblocks + mb) * 128 + m];
       }
-    }
     }
   }
   tc_fence_before();
@@ -260,16 +280,17 @@ int b2no_tc_wgrad(const float* g, const float* x, float* partial, int max_blocks
   WgLayout L;
   bool ok = false;
   p.SUB = p.mblocks == 1 ? 64 : 32;
-  if (wg_tmem_cols(p) > 512) return 1;
-  // long contiguous runs per channel row (TP px = 4 TP bytes) matter for DRAM page locality: 256-byte runs measured 1.8 TB/s
-  for (p.TP = 256; p.TP >= p.SUB && !ok; p.TP >>= 1) {
-    if (pixels % p.TP != 0) continue;
-    for (p.S = 8; p.S >= 3; p.S--) {
-      L = wg_layout(p);
-      if ((int)L.total <= max_smem) { ok = true; break; }
+  if (p.mblocks > 3 || wg_tmem_cols(p) > 512) return 1;
+  // bytes in flight decide an HBM-bound kernel: take the largest tile that still leaves >= 4 stages, else the deepest ring
+  for (int pass = 0; pass < 2 && !ok; pass++)
+    for (p.TP = 256; p.TP >= p.SUB && !ok; p.TP >>= 1) {
+      if (pixels % p.TP != 0) continue;
+      for (p.S = 8; p.S >= (pass == 0 ? 4 : 2); p.S--) {
+        L = wg_layout(p);
+        if ((int)L.total <= max_smem) { ok = true; break; }
+      }
+      if (ok) break;
     }
-    if (ok) break;
-  }
   if (!ok) return 1;
   p.nb = p.TP / 32;
   p.tiles_per_img = (int)(pixels / p.TP);

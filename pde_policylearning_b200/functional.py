@@ -103,21 +103,24 @@ class FNOStackFn(torch.autograd.Function):
     layers: the dx pass of layer l multiplies by act'(z_{l-1}) in its epilogue and so emits gz_{l-1} directly -- no
     separate activation-backward pass over the activations.
 
-    params = for each layer: bias (Co,) | pw_w (Co, Ci, 1...) | n_corners corner tensors."""
+    bias_all = the (n_layers, Co, 1, ...) bias parameter of the conv stack (spectral_convolution.py:271-272), taken whole
+    so that its gradient is written once by the weight-gradient kernels instead of being assembled from per-layer
+    slices; params = for each layer: pw_w (Co, Ci, 1...) | n_corners corner tensors."""
 
     @staticmethod
-    def forward(ctx, x, geom: SpecGeom, acts, n_corners, *params):
+    def forward(ctx, x, geom: SpecGeom, acts, n_corners, bias_all, *params):
         ops._require_cuda(x)
         x = _contig(x.float())
         plan = get_plan(geom, x.device)
-        per = 2 + n_corners
+        per = 1 + n_corners
         L = len(params) // per
         need_grad = any(ctx.needs_input_grad)
         saved, meta = [], []
         cur = x
+        b2d = _contig(bias_all.detach().reshape(L, -1).float())
         for l in range(L):
-            bias, pw_w = params[l * per], params[l * per + 1]
-            det = [c.detach() for c in params[l * per + 2:(l + 1) * per]]
+            pw_w = params[l * per]
+            det = [c.detach() for c in params[l * per + 1:(l + 1) * per]]
             B, ci = cur.shape[:2]
             co = det[0].shape[1]
             xh = ops.dft_forward(plan, 0, cur)
@@ -126,12 +129,13 @@ class FNOStackFn(torch.autograd.Function):
             need_z = act not in (None, "none") and need_grad
             z = torch.empty((B, co) + tuple(plan.geom.nout), dtype=torch.float32, device=x.device) if need_z else None
             pw2d = _contig(pw_w.detach().reshape(pw_w.shape[0], -1).float())
-            epi = ops.make_epilogue(bias=_contig(bias.detach().reshape(-1).float()), pw_w=pw2d, pw_x=cur, preact=z, act=act)
+            epi = ops.make_epilogue(bias=b2d[l], pw_w=pw2d, pw_x=cur, preact=z, act=act)
             y = ops.dft_inverse(plan, 0, yh, epi)
             saved += [cur, xh, z if z is not None else cur.new_empty(0), pw2d] + det
-            meta.append((tuple(bias.shape), tuple(pw_w.shape), ci, co, need_z))
+            meta.append((tuple(pw_w.shape), ci, co, need_z))
             cur = y
         ctx.geom, ctx.acts, ctx.n_corners, ctx.meta = geom, acts, n_corners, meta
+        ctx.bias_shape = tuple(bias_all.shape)
         ctx.save_for_backward(*saved)
         return cur
 
@@ -142,42 +146,44 @@ class FNOStackFn(torch.autograd.Function):
         per_s = 4 + nc
         L = len(meta)
         plan = get_plan(geom, gy.device)
-        per = 2 + nc
+        per = 1 + nc
         grads = [None] * (L * per)
+        need_bias = ctx.needs_input_grad[4]
+        dbias = gy.new_empty((L, meta[0][2])) if need_bias else None
         g = _contig(gy.float())
         # top layer: gradient w.r.t. its pre-activation
-        if meta[L - 1][4]:
+        if meta[L - 1][3]:
             g = ops.act_bwd(g, saved[(L - 1) * per_s + 2], acts[L - 1])
         for l in range(L - 1, -1, -1):
             x, xh, _, pw2d = saved[l * per_s: l * per_s + 4]
             det = list(saved[l * per_s + 4: (l + 1) * per_s])
-            bias_shape, pw_shape, ci, co, _ = meta[l]
-            need = ctx.needs_input_grad[4 + l * per: 4 + (l + 1) * per]
+            pw_shape, ci, co, _ = meta[l]
+            need = ctx.needs_input_grad[5 + l * per: 5 + (l + 1) * per]
             gyh = ops.dft_forward(plan, 1, g)
-            if any(need[2:]):
+            if any(need[1:]):
                 dcs = ops.mix_dw(plan, xh, gyh, det, needs_zero=_geom_has_overlap(geom))
                 for j in range(nc):
-                    grads[l * per + 2 + j] = dcs[j]
-            if need[0] or need[1]:
-                dpw, db = ops.pw_wgrad(g, x, need_bias=need[0])
-                grads[l * per + 1] = dpw.reshape(pw_shape)
-                if need[0]:
-                    grads[l * per] = db.reshape(bias_shape)
+                    grads[l * per + 1 + j] = dcs[j]
+            if need_bias or need[0]:
+                dpw, _ = ops.pw_wgrad(g, x, need_bias=need_bias, db_out=dbias[l] if need_bias else None)
+                grads[l * per] = dpw.reshape(pw_shape)
             if l > 0 or ctx.needs_input_grad[0]:
                 gxh = ops.mix(plan, 1, gyh, det, ci, co)
-                zprev = saved[(l - 1) * per_s + 2] if (l > 0 and meta[l - 1][4]) else None
+                zprev = saved[(l - 1) * per_s + 2] if (l > 0 and meta[l - 1][3]) else None
                 epi = ops.make_epilogue(pw_w=pw2d, pw_x=g, pw_transposed=True, dact_z=zprev,
                                         dact=acts[l - 1] if zprev is not None else None)
                 g = ops.dft_inverse(plan, 1, gxh, epi)
-        return (g if ctx.needs_input_grad[0] else None, None, None, None) + tuple(grads)
+        return (g if ctx.needs_input_grad[0] else None, None, None, None,
+                dbias.reshape(ctx.bias_shape) if need_bias else None) + tuple(grads)
 
 
-def fno_stack(x, geom: SpecGeom, layers, acts):
-    """layers: list of (bias, pw_weight, [corners]); acts: activation name (or None) per layer."""
+def fno_stack(x, geom: SpecGeom, bias_all, layers, acts):
+    """bias_all: (n_layers, Co, 1, ...) bias of the conv stack; layers: list of (pw_weight, [corners]); acts: activation
+    name (or None) per layer."""
     flat = []
-    for bias, pw_w, corners in layers:
-        flat += [bias, pw_w] + list(corners)
-    return FNOStackFn.apply(x, geom, tuple(acts), len(layers[0][2]), *flat)
+    for pw_w, corners in layers:
+        flat += [pw_w] + list(corners)
+    return FNOStackFn.apply(x, geom, tuple(acts), len(layers[0][1]), bias_all, *flat)
 
 
 class PointwiseConvFn(torch.autograd.Function):
@@ -334,7 +340,8 @@ def mlp_head(x, w1, b1, w2, b2, act="gelu"):
 
 
 class RelL2Fn(torch.autograd.Function):
-    """LpLoss.rel with p=2 (libs/utilities3.py:323-334): sum_b or mean_b of ||x_b - y_b|| / ||y_b||."""
+    """LpLoss.rel with p=2 (libs/utilities3.py:323-334): sum_b or mean_b of ||x_b - y_b|| / ||y_b||.  Three launches in
+    all: per-sample sums, the scalar tail (sqrt, ratio, sum) on the device, and dx = g coef_b (x - y)."""
 
     @staticmethod
     def forward(ctx, x, y, size_average):
@@ -342,21 +349,15 @@ class RelL2Fn(torch.autograd.Function):
         B = x.shape[0]
         xf, yf = _contig(x.float()).reshape(B, -1), _contig(y.float()).reshape(B, -1)
         sums = ops.rel_l2_sums(xf, yf)
-        d, n = sums[:, 0].sqrt(), sums[:, 1].sqrt()
-        ctx.save_for_backward(xf, yf, d, n)
-        ctx.size_average = size_average
+        loss, coef = ops.rel_l2_finish(sums, bool(size_average))
+        ctx.save_for_backward(xf, yf, coef)
         ctx.x_shape = tuple(x.shape)
-        r = d / n
-        return r.mean() if size_average else r.sum()
+        return loss
 
     @staticmethod
     def backward(ctx, g):
-        xf, yf, d, n = ctx.saved_tensors
-        B = xf.shape[0]
-        coef = g / (d * n)
-        if ctx.size_average:
-            coef = coef / B
-        dx = ops.rel_l2_bwd(xf, yf, _contig(coef.float()))
+        xf, yf, coef = ctx.saved_tensors
+        dx = ops.rel_l2_bwd_g(xf, yf, coef, _contig(g.float()))
         return dx.reshape(ctx.x_shape), None, None
 
 

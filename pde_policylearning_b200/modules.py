@@ -383,8 +383,8 @@ class FNO(nn.Module):
             convs = blocks.convs
             geom = convs._geom(tuple(x.shape[2:]), 0)
             acts = [(_act_name(blocks.non_linearity) if i < (blocks.n_layers - i) else None) for i in range(self.n_layers)]
-            layers = [(convs.bias[i].reshape(-1), blocks.fno_skips[i].weight, convs.corners(i)) for i in range(self.n_layers)]
-            x = Fn.fno_stack(x, geom, layers, acts)
+            layers = [(blocks.fno_skips[i].weight, convs.corners(i)) for i in range(self.n_layers)]
+            x = Fn.fno_stack(x, geom, convs.bias, layers, acts)
         else:
             for layer_idx in range(self.n_layers):
                 x = self.fno_blocks(x, layer_idx)

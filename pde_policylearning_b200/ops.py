@@ -265,8 +265,8 @@ def act_bwd(gy: torch.Tensor, z: torch.Tensor, act) -> torch.Tensor:
     return gz
 
 
-def pw_wgrad(g: torch.Tensor, x: torch.Tensor, need_bias: bool):
-    """g (B, Co, *grid), x (B, Ci, *grid) -> dW (Co, Ci), db (Co) | None."""
+def pw_wgrad(g: torch.Tensor, x: torch.Tensor, need_bias: bool, db_out: Optional[torch.Tensor] = None):
+    """g (B, Co, *grid), x (B, Ci, *grid) -> dW (Co, Ci), db (Co) | None.  db_out: contiguous (Co,) destination for db."""
     B, co = g.shape[:2]
     ci = x.shape[1]
     P = math.prod(g.shape[2:])
@@ -274,7 +274,10 @@ def pw_wgrad(g: torch.Tensor, x: torch.Tensor, need_bias: bool):
     n = int(L.b2no_pw_wgrad_scratch_floats(ci, co))
     partial = torch.empty(n, dtype=torch.float32, device=g.device)
     dw = torch.empty((co, ci), dtype=torch.float32, device=g.device)
-    db = torch.empty((co,), dtype=torch.float32, device=g.device) if need_bias else None
+    db = None
+    if need_bias:
+        db = db_out if db_out is not None else torch.empty((co,), dtype=torch.float32, device=g.device)
+        assert db.is_contiguous() and db.numel() == co and db.dtype == torch.float32
     check(L.b2no_pw_wgrad(_ptr(g), _ptr(x), _ptr(dw), _ptr(db), _ptr(partial), B, ci, co, P, _stream()), "pw_wgrad")
     LAUNCHES[0] += 2
     return dw, db
@@ -349,3 +352,31 @@ def rel_l2_bwd(x, y, coef):
     check(_lib.lib().b2no_rel_l2_bwd(_ptr(x), _ptr(y), _ptr(coef), _ptr(dx), B, x.numel() // B, _stream()), "rel_l2_bwd")
     LAUNCHES[0] += 1
     return dx
+
+
+def rel_l2_finish(sums, size_average: bool):
+    """sums (B, 2) -> (loss scalar tensor, coef (B,)): the tail of LpLoss.rel on the device, one launch."""
+    B = sums.shape[0]
+    loss = torch.empty((), dtype=torch.float32, device=sums.device)
+    coef = torch.empty((B,), dtype=torch.float32, device=sums.device)
+    check(_lib.lib().b2no_rel_l2_finish(_ptr(sums), _ptr(loss), _ptr(coef), B, 1 if size_average else 0, _stream()),
+          "rel_l2_finish")
+    LAUNCHES[0] += 1
+    return loss, coef
+
+
+def rel_l2_bwd_g(x, y, coef, g):
+    """dx = g * coef[b] * (x - y), g a 0-dim device tensor (the upstream gradient)."""
+    B = x.shape[0]
+    dx = torch.empty_like(x)
+    check(_lib.lib().b2no_rel_l2_bwd_g(_ptr(x), _ptr(y), _ptr(coef), _ptr(g), _ptr(dx), B, x.numel() // B, _stream()),
+          "rel_l2_bwd_g")
+    LAUNCHES[0] += 1
+    return dx
+
+
+def gather_segments(flat, ptr_table, offsets, counts, nseg: int):
+    check(_lib.lib().b2no_gather_segments(_ptr(flat), _ptr(ptr_table), _ptr(offsets), _ptr(counts), nseg, _stream()),
+          "gather_segments")
+    LAUNCHES[0] += 1
+

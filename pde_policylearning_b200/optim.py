@@ -47,9 +47,24 @@ class FusedAdam:
         self.step_counter = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def zero_grad(self, set_to_none: bool = False):
-        self.bucket.zero()
+        """set_to_none: drop the gradients, so that the next backward assigns them and `sync_grads()` collects
+        them with one kernel; False: zero the flat bucket in place (gradients then accumulate into it, as torch does)."""
+        if set_to_none:
+            self.bucket.release_grads()
+        else:
+            for p, v in zip(self.bucket.params, self.bucket._views()):
+                p.grad = v
+            self.bucket.zero()
+
+    def sync_grads(self, group=None):
+        """After backward: gather the per-parameter gradients into the flat bucket and (world > 1) sum them over the
+        ranks with ONE all-reduce; `step(grad_scale=1/world)` turns the sum into the data-parallel mean."""
+        self.bucket.gather()
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.SUM, group=group)
 
     def step(self, grad_scale: float = 1.0):
+        self.bucket.gather()           # no-op when the gradients already live in the flat bucket
         L = _lib.lib()
         _lib.check(L.b2no_adam_step(ops._ptr(self.flat_param), ops._ptr(self.bucket.flat), ops._ptr(self.exp_avg),
                                     ops._ptr(self.exp_avg_sq), self.bucket.numel, ops._ptr(self.step_counter),
@@ -104,12 +119,11 @@ class GraphedTrainStep:
             dst.copy_(src)
 
     def _eager(self):
-        self.opt.zero_grad()
+        self.opt.zero_grad(set_to_none=True)
         out = self.model(*self.static_in)
         loss = self.loss_fn(out, self.static_tgt)
         loss.backward()
-        if self.world > 1:
-            dist.all_reduce(self.opt.bucket.flat, op=dist.ReduceOp.SUM, group=self.group)
+        self.opt.sync_grads(self.group)
         self.opt.step(grad_scale=1.0 / self.world)
         return loss.detach()
 

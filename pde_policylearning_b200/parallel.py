@@ -71,6 +71,71 @@ class GradBucket:
         if self.flat is not None:
             self.flat.zero_()
 
+    def _views(self):
+        if getattr(self, "_view_cache", None) is None or self._view_cache[0] is not self.flat:
+            views = []
+            for p, off in zip(self.params, self.offsets):
+                n = (2 if p.is_complex() else 1) * p.numel()
+                chunk = self.flat[off: off + n]
+                views.append(torch.view_as_complex(chunk.view(*p.shape, 2)) if p.is_complex() else chunk.view(p.shape))
+            self._view_cache = (self.flat, views)
+        return self._view_cache[1]
+
+    def release_grads(self):
+        """p.grad = None for every parameter: the next backward then ASSIGNS its gradient tensors (no `grad += g`
+        kernel per parameter); `gather()` collects them into the flat bucket with one launch."""
+        for p in self.params:
+            p.grad = None
+
+    def gather(self):
+        """Copy whatever gradient tensors the backward left in p.grad into the flat bucket (ONE kernel over a device
+        pointer table; missing gradients become zeros) and make p.grad views of the bucket again.  CUDA only.
+        Inside a CUDA-graph capture the pointer table is captured with the graph (the gradient tensors live in the
+        graph's private pool, so their addresses are the same at every replay)."""
+        from . import ops
+        if self.flat is None:
+            self.attach()
+            return self.flat
+        views = self._views()
+        nseg = len(self.params)
+        dev = self.flat.device
+        if getattr(self, "_seg_dev", None) is None:
+            offs = list(self.offsets) + [self.numel]
+            cnts = [(2 if p.is_complex() else 1) * p.numel() for p in self.params]
+            self._seg_dev = (torch.tensor(offs, dtype=torch.int64, device=dev), torch.tensor(cnts, dtype=torch.int64, device=dev))
+            self._ptr_dev = torch.zeros(nseg, dtype=torch.int64, device=dev)
+            self._keep = []
+        ptrs, keep, in_place = [], [], True
+        for p, v in zip(self.params, views):
+            g = p.grad
+            if g is None:
+                ptrs.append(0)
+                in_place = False
+                continue
+            if g.device != dev or g.dtype != p.dtype:
+                raise RuntimeError("GradBucket.gather: gradient on the wrong device / of the wrong dtype")
+            if not g.is_contiguous():
+                g = g.contiguous()
+            keep.append(g)
+            ptrs.append(g.data_ptr())
+            in_place = in_place and g.data_ptr() == v.data_ptr()
+        if not in_place:
+            host = torch.tensor(ptrs, dtype=torch.int64).pin_memory()
+            capturing = torch.cuda.is_current_stream_capturing()
+            # the host table must stay untouched for as long as a captured graph may replay the copy
+            (self._keep if capturing else keep).append(host)
+            if capturing:
+                self._keep.extend(keep)
+            self._ptr_dev.copy_(host, non_blocking=True)
+            ops.gather_segments(self.flat, self._ptr_dev, self._seg_dev[0], self._seg_dev[1], nseg)
+            if not capturing:
+                # eager: the source tensors / host table may be freed once the copy + kernel are enqueued only because
+                # the caching allocators are stream-ordered; keep them until the next call to be explicit
+                self._last = keep
+        for p, v in zip(self.params, views):
+            p.grad = v
+        return self.flat
+
     def allreduce_mean(self, group=None):
         if self.flat is None:
             self.attach()

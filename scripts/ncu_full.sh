@@ -8,6 +8,7 @@ for what in "$@"; do
     fwd)   k="k_r2c_last|k_cmat|k_fwd_tc"; skip=1; cnt=1;;
     inv)   k="k_pw_tc|k_inv_h"; skip=2; cnt=2;;
     invgelu) k="k_pw_tc"; skip=1; cnt=1;;
+    inv3)  k="k_pw_tc"; skip=1; cnt=1;;
     wgrad) k="k_wgrad_tc"; skip=1; cnt=1;;
     invh)  k="k_inv_h"; skip=1; cnt=1; what2=inv;;
   esac

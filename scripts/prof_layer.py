@@ -12,7 +12,7 @@ x = torch.randn(B, C, N, N, device=dev)
 yh = torch.randn(B, C, *plan.kept, dtype=torch.complex64, device=dev)
 w = torch.randn(C, C, device=dev)
 bias = torch.randn(C, device=dev)
-z = torch.empty_like(x)
+z = torch.randn_like(x)
 what = sys.argv[1] if len(sys.argv) > 1 else "all"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 for _ in range(iters):
@@ -22,6 +22,8 @@ for _ in range(iters):
         y = ops.dft_inverse(plan, 0, yh, ops.make_epilogue(bias=bias, pw_w=w, pw_x=x))
     if what in ("all", "invgelu"):
         y = ops.dft_inverse(plan, 0, yh, ops.make_epilogue(bias=bias, pw_w=w, pw_x=x, preact=z, act="gelu"))
+    if what in ("all", "inv3"):
+        y = ops.dft_inverse(plan, 1, yh, ops.make_epilogue(pw_w=w, pw_x=x, pw_transposed=True, dact_z=z, dact="gelu"))
     if what in ("all", "wgrad"):
         ops.pw_wgrad(z, x, need_bias=False)
 if what in ("all", "mlp"):
@@ -51,6 +53,7 @@ if what == "time":
 ("fwd", lambda: ops.dft_forward(plan, 0, x)),
                      ("inv", lambda: ops.dft_inverse(plan, 0, yh, ops.make_epilogue(bias=bias, pw_w=w, pw_x=x))),
                      ("invgelu", lambda: ops.dft_inverse(plan, 0, yh, ops.make_epilogue(bias=bias, pw_w=w, pw_x=x, preact=z, act="gelu"))),
+                     ("inv3", lambda: ops.dft_inverse(plan, 1, yh, ops.make_epilogue(pw_w=w, pw_x=x, pw_transposed=True, dact_z=z, dact="gelu"))),
                      ("wgrad", lambda: ops.pw_wgrad(z, x, need_bias=False))):
         for _ in range(3):
             fn()

@@ -201,6 +201,67 @@ __global__ void __launch_bounds__(128) k_t3(const float* __restrict__ A, const f
 }
 
 // -------------------------------------------------------------------------------------------------
+// T6 / T7: MN-major NO-swizzle ("interleave") operands.  Element (mn, k) of an operand lives at
+//     (mn / 4) * mn_stride + (k / 8) * k_stride + (k % 8) * 16 + (mn % 4) * 4            (bytes)
+// i.e. 16-byte groups of 4 MN-contiguous elements, 8 consecutive k at a 16-byte pitch.  `swap` selects which of the
+// two strides goes into the descriptor's LBO field.  amn / bmn: operand is MN-major (else K-major no-swizzle).
+// -------------------------------------------------------------------------------------------------
+template <int N, int K>
+__global__ void __launch_bounds__(128) k_t6(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D,
+                                            int amn, int bmn, int swap, int a_mn_stride, int a_k_stride, int b_mn_stride,
+                                            int b_k_stride) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sA = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = sA + 128 * K * 4;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 128 * K; i += 128) {
+    const int r = i / K, k = i % K;
+    const uint32_t off = amn ? (uint32_t)((r / 4) * a_mn_stride + (k / 8) * a_k_stride + (k % 8) * 16 + (r % 4) * 4) : kmajor_off(r, k, K);
+    *(float*)(sA + off) = A[i];
+  }
+  for (int i = tid; i < N * K; i += 128) {
+    const int r = i / K, k = i % K;
+    const uint32_t off = bmn ? (uint32_t)((r / 4) * b_mn_stride + (k / 8) * b_k_stride + (k % 8) * 16 + (r % 4) * 4) : kmajor_off(r, k, K);
+    *(float*)(sB + off) = B[i];
+  }
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  fence_proxy_async();
+  if (warp == 0) tmem_alloc(&tslot, 32 > N ? 32 : N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tslot;
+  if (tid == 0) {
+    const uint32_t idesc = idesc_tf32(128, N, amn, bmn);
+    const uint32_t sbo = (K / 4) * 128;
+    for (int k = 0; k < K / 8; k++) {
+      uint64_t da, db;
+      if (amn) da = swap ? smem_desc(smem_u32(sA) + k * a_k_stride, a_mn_stride, a_k_stride, LAYOUT_NONE)
+                         : smem_desc(smem_u32(sA) + k * a_k_stride, a_k_stride, a_mn_stride, LAYOUT_NONE);
+      else da = smem_desc(smem_u32(sA) + k * 256, 128, sbo, LAYOUT_NONE);
+      if (bmn) db = swap ? smem_desc(smem_u32(sB) + k * b_k_stride, b_mn_stride, b_k_stride, LAYOUT_NONE)
+                         : smem_desc(smem_u32(sB) + k * b_k_stride, b_k_stride, b_mn_stride, LAYOUT_NONE);
+      else db = smem_desc(smem_u32(sB) + k * 256, 128, sbo, LAYOUT_NONE);
+      mma_tf32_ss(tbase, da, db, idesc, k > 0);
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  float v[16];
+  for (int c = 0; c < N; c += 16) {
+    tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + c, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; j++) D[(size_t)tid * N + c + j] = v[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, 32 > N ? 32 : N);
+}
+
+// -------------------------------------------------------------------------------------------------
 static float trunc_tf32(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; }
 static float rna_tf32(float x) {
   uint32_t u; memcpy(&u, &x, 4);
@@ -307,6 +368,42 @@ int main() {
       printf("T%d TS (A in TMEM), B %s : rel err vs trunc %.3e  vs rna %.3e  vs exact %.3e\n", bsw ? 4 : 3,
              bsw ? "K-major SW128 " : "K-major no-swz", e.trunc, e.rna, e.exact);
     }
+  }
+
+  // ---------------- T6 / T7: MN-major no-swizzle operands ----------------
+  {
+    constexpr int N = 32, K = 128;
+    std::vector<float> A(128 * K), B(N * K), D(128 * N);
+    for (auto& v : A) v = frand();
+    for (auto& v : B) v = frand();
+    float *dA, *dB, *dD;
+    CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4));
+    CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+    const int smem = (128 + N) * K * 4 + 1024;
+    CK(cudaFuncSetAttribute(k_t6<N, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    struct Case { const char* name; int amn, bmn, a_mn, a_k, b_mn, b_k; };
+    // a: F-tile style (k groups dense at 128 B, MN groups at (K/8)*128);  b: K-major image reinterpreted (MN groups at 128 B, k groups at (MN/4)*128)
+    const Case cases[] = {
+        {"sanity: both K-major ", 0, 0, 0, 0, 0, 0},
+        {"A MN-major (k-dense) ", 1, 0, (K / 8) * 128, 128, 0, 0},
+        {"A MN-major (mn-dense)", 1, 0, 128, (128 / 4) * 128, 0, 0},
+        {"B MN-major (k-dense) ", 0, 1, 0, 0, (K / 8) * 128, 128},
+        {"B MN-major (mn-dense)", 0, 1, 0, 0, 128, (N / 4) * 128},
+        {"A+B MN-major         ", 1, 1, (K / 8) * 128, 128, 128, (N / 4) * 128},
+    };
+    for (const Case& c : cases)
+      for (int swap = 0; swap < 2; swap++) {
+        CK(cudaMemset(dD, 0, D.size() * 4));
+        k_t6<N, K><<<1, 128, smem>>>(dA, dB, dD, c.amn, c.bmn, swap, c.a_mn, c.a_k, c.b_mn, c.b_k);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+        Err e = compare(D, 128, N, K, [&](int m, int k) { return A[m * K + k]; }, [&](int n, int k) { return B[n * K + k]; });
+        printf("   D[0..3] = %g %g %g %g   D[5*N+7] = %g\n", D[0], D[1], D[2], D[3], D[5 * N + 7]);
+        printf("T6 %s no-swizzle, %s : rel err vs trunc %.3e  vs exact %.3e\n", c.name,
+               swap ? "LBO = MN-group stride, SBO = k-group stride" : "LBO = k-group stride, SBO = MN-group stride", e.trunc, e.exact);
+      }
   }
   printf("probe done\n");
   return 0;
