@@ -309,10 +309,10 @@ def run_b200(args):
     res_in = (graphed.static_in[0], graphed.static_tgt) if graphed is not None else (p_dev, t_dev)
     for _ in range(args.warmup):
         step(*res_in)
-    l0 = ops.LAUNCHES[0]
+    l0 = ops.launch_count()
     with ClockSampler(local_rank) as clk:
         ms = timed(lambda: step(*res_in), args.steps)
-    launches = (ops.LAUNCHES[0] - l0) // args.steps
+    launches = (ops.launch_count() - l0) // args.steps
     clocks = clk.summary()
     ms_per_step = ms / args.steps
     value = BATCH * world / (ms_per_step * 1e-3)
@@ -370,11 +370,23 @@ def run_b200(args):
                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                "roofline": roofline, "cpu_baseline": cpu}
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     if out is not None:
-        print(json.dumps(out))
+        emit(json.dumps(out))
+    if world > 1:
+        # tear down: the captured graph holds NCCL work, and destroying the communicator under a live graph blocks
+        # (seen on 2 GPUs) -- release the graph first, and never let the teardown outlive the result
+        dist.barrier()
+        if graphed is not None:
+            graphed.graph.reset()
+            graphed = None
+        torch.cuda.synchronize()
+        t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        t.start()
+        t.join(20.0)
+        if t.is_alive():
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
 
 
 def run_reference(args):
@@ -390,10 +402,30 @@ def run_reference(args):
            "config": config_dict(args.gpus),
            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
            "e2e": {"value": round(r["value"], 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(json.dumps(out))
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings) was sent to stderr."""
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, (line + "\n").encode())
+    else:
+        print(line, flush=True)
 
 
 def main():
+    global _REAL_STDOUT
+    # keep stdout clean for the JSON line: libraries (NCCL prints its version banner on stdout) write to fd 1
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+    if os.environ.get("B2NO_HANG_DUMP_S"):
+        # debugging aid: dump every thread's Python stack (and exit) if the run is still going after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["B2NO_HANG_DUMP_S"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

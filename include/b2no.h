@@ -174,6 +174,10 @@ int b2no_rel_l2_bwd_g(const float* x, const float* y, const float* coef, const f
  * step_counter is a DEVICE int incremented by the call, so a captured CUDA graph replays correctly. */
 int b2no_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int* step_counter,
                    float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream);
+/* number of kernels this library has launched so far in this process (host-side counter; kernels replayed from a
+ * captured CUDA graph are not seen by it) */
+int64_t b2no_kernel_launches(void);
+
 /* flat[offsets[s] .. offsets[s+1]) = src_ptrs[s][0 .. counts[s]) (zero fill beyond counts[s] or when src_ptrs[s] is
  * null): the per-parameter gradients autograd produced, gathered into the flat bucket the all-reduce and
  * b2no_adam_step work on.  src_ptrs (nseg device pointers), offsets (nseg + 1) and counts (nseg) are DEVICE arrays.

@@ -10,10 +10,13 @@
     if (_e != cudaSuccess) return (int)_e;         \
   } while (0)
 
+// every kernel launch of the library is followed by this check; it also counts the launch (b2no_kernel_launches)
+extern long long g_b2no_launches;
 #define B2NO_LAUNCH_CHECK()                        \
   do {                                             \
     cudaError_t _e = cudaGetLastError();           \
     if (_e != cudaSuccess) return (int)_e;         \
+    g_b2no_launches++;                             \
   } while (0)
 
 static inline int b2no_ceil_div(long a, long b) { return (int)((a + b - 1) / b); }

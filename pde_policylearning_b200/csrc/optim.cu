@@ -52,6 +52,7 @@ extern "C" int b2no_adam_step(float* param, const float* grad, float* exp_avg, f
   if (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) return B2NO_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   k_adam_tick<<<1, 1, 0, st>>>(step_counter);
+  B2NO_LAUNCH_CHECK();
   long blocks = ((n + 3) / 4 + 255) / 256;
   const long cap = (long)b2no_sm_count() * 8;
   if (blocks > cap) blocks = cap;

@@ -8,6 +8,9 @@
 #include "common.cuh"
 
 static int g_sm_count[64];
+long long g_b2no_launches = 0;
+extern "C" int64_t b2no_kernel_launches(void) { return (int64_t)g_b2no_launches; }
+
 int b2no_sm_count() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;

@@ -26,14 +26,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// The wait suspends the warp in hardware for up to kMbarSuspendNs before the instruction returns false (PTX: the optional
+// suspendTimeHint of mbarrier.try_wait).  Without the hint a waiting warp came back every ~30 ns: in the persistent
+// kernels here a quarter of all issued instructions were TRYWAIT / BRA / YIELD of warps that had nothing to do, taken
+// from the issue slots of the epilogue warps sharing their scheduler.
+constexpr uint32_t kMbarSuspendNs = 20000;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendNs)
       : "memory");
   return ok != 0;
 }

@@ -13,8 +13,14 @@ from . import _lib
 from ._lib import ACT, NORM, Epilogue, Geom, Weights, check
 
 
-# number of libb2no kernels launched so far (bench.py reports the per-step count as `gpu_launches`)
-LAUNCHES = [0]
+# kernels replayed from captured CUDA graphs (the C-side counter only sees direct launches)
+_REPLAYED = [0]
+
+
+def launch_count() -> int:
+    """Number of libb2no kernels launched so far, graph replays included (bench.py reports the per-step count as
+    `gpu_launches`)."""
+    return int(_lib.lib().b2no_kernel_launches()) + _REPLAYED[0]
 
 
 def set_tensor_core_mode(on: bool) -> bool:
@@ -175,7 +181,6 @@ def dft_forward(plan: Plan, which: int, x: torch.Tensor) -> torch.Tensor:
     work = plan.workspace(B, Cc)
     check(_lib.lib().b2no_dft_forward(plan.handle, which, _ptr(x), _ptr(spec), _ptr(work), B * Cc, _stream()),
           "dft_forward")
-    LAUNCHES[0] += plan.geom.ndim
     return spec
 
 
@@ -216,7 +221,6 @@ def dft_inverse(plan: Plan, which: int, spec: torch.Tensor, epi: Optional[Epilog
     check(_lib.lib().b2no_dft_inverse(plan.handle, which, _ptr(spec), _ptr(y), _ptr(work), B, Cc,
                                       math.prod(grid), C.byref(epi) if epi is not None else None, _stream()),
           "dft_inverse")
-    LAUNCHES[0] += plan.geom.ndim
     return y
 
 
@@ -225,7 +229,6 @@ def pointwise(batch: int, channels: int, grid: Tuple[int, ...], device, epi: Epi
     y = torch.empty((batch, channels) + tuple(grid), dtype=torch.float32, device=device)
     check(_lib.lib().b2no_dft_inverse(None, 0, None, _ptr(y), None, batch, channels, math.prod(grid),
                                       C.byref(epi), _stream()), "pointwise")
-    LAUNCHES[0] += 1
     return y
 
 
@@ -242,7 +245,6 @@ def mix(plan: Plan, mode: int, spec: torch.Tensor, corners: Sequence[torch.Tenso
     w = weights_struct(corners, plan.geom.ndim)
     check(_lib.lib().b2no_mix(plan.handle, mode, _ptr(spec), C.byref(w), _ptr(out), B, ci, co,
                               1 if accumulate else 0, _stream()), "mix")
-    LAUNCHES[0] += 1
     return out
 
 
@@ -254,14 +256,12 @@ def mix_dw(plan: Plan, xh: torch.Tensor, gyh: torch.Tensor, like: Sequence[torch
     grads = [alloc(t, memory_format=torch.contiguous_format) for t in like]
     w = weights_struct(grads, plan.geom.ndim)
     check(_lib.lib().b2no_mix_dw(plan.handle, _ptr(xh), _ptr(gyh), C.byref(w), B, ci, co, 0, _stream()), "mix_dw")
-    LAUNCHES[0] += 1
     return grads
 
 
 def act_bwd(gy: torch.Tensor, z: torch.Tensor, act) -> torch.Tensor:
     gz = torch.empty_like(gy)
     check(_lib.lib().b2no_act_bwd(_ptr(gy), _ptr(z), _ptr(gz), gy.numel(), ACT[act], _stream()), "act_bwd")
-    LAUNCHES[0] += 1
     return gz
 
 
@@ -279,7 +279,6 @@ def pw_wgrad(g: torch.Tensor, x: torch.Tensor, need_bias: bool, db_out: Optional
         db = db_out if db_out is not None else torch.empty((co,), dtype=torch.float32, device=g.device)
         assert db.is_contiguous() and db.numel() == co and db.dtype == torch.float32
     check(L.b2no_pw_wgrad(_ptr(g), _ptr(x), _ptr(dw), _ptr(db), _ptr(partial), B, ci, co, P, _stream()), "pw_wgrad")
-    LAUNCHES[0] += 2
     return dw, db
 
 
@@ -291,7 +290,6 @@ def mlp_head_fwd(x, w1, b1, w2, b2, act="gelu") -> torch.Tensor:
     out = torch.empty((B, 1) + grid, dtype=torch.float32, device=x.device)
     check(_lib.lib().b2no_mlp_head_fwd(_ptr(x), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(out), B, ci, hidden,
                                        math.prod(grid), 1 if per_sample else 0, ACT[act], _stream()), "mlp_head_fwd")
-    LAUNCHES[0] += 1
     return out
 
 
@@ -318,14 +316,12 @@ def mlp_head_bwd(x, w1, b1, w2, g, act="gelu", want_gz=True, dact_z=None, dact=N
     if rc == -2:
         return None
     check(rc, "mlp_head_bwd")
-    LAUNCHES[0] += 2
     return gx, gz, dw2
 
 
 def rno_gate_fwd(z, z2, hh, h):
     out = torch.empty_like(h)
     check(_lib.lib().b2no_rno_gate_fwd(_ptr(z), _ptr(z2), _ptr(hh), _ptr(h), _ptr(out), h.numel(), _stream()), "gate")
-    LAUNCHES[0] += 1
     return out
 
 
@@ -333,7 +329,6 @@ def rno_gate_bwd(g, z, z2, hh, h):
     outs = [torch.empty_like(h) for _ in range(4)]
     check(_lib.lib().b2no_rno_gate_bwd(_ptr(g), _ptr(z), _ptr(z2), _ptr(hh), _ptr(h), *[_ptr(o) for o in outs],
                                        h.numel(), _stream()), "gate_bwd")
-    LAUNCHES[0] += 1
     return outs
 
 
@@ -342,7 +337,6 @@ def rel_l2_sums(x, y):
     n = x.numel() // B
     sums = torch.empty((B, 2), dtype=torch.float32, device=x.device)
     check(_lib.lib().b2no_rel_l2_sums(_ptr(x), _ptr(y), _ptr(sums), B, n, _stream()), "rel_l2_sums")
-    LAUNCHES[0] += 1
     return sums
 
 
@@ -350,7 +344,6 @@ def rel_l2_bwd(x, y, coef):
     B = x.shape[0]
     dx = torch.empty_like(x)
     check(_lib.lib().b2no_rel_l2_bwd(_ptr(x), _ptr(y), _ptr(coef), _ptr(dx), B, x.numel() // B, _stream()), "rel_l2_bwd")
-    LAUNCHES[0] += 1
     return dx
 
 
@@ -361,7 +354,6 @@ def rel_l2_finish(sums, size_average: bool):
     coef = torch.empty((B,), dtype=torch.float32, device=sums.device)
     check(_lib.lib().b2no_rel_l2_finish(_ptr(sums), _ptr(loss), _ptr(coef), B, 1 if size_average else 0, _stream()),
           "rel_l2_finish")
-    LAUNCHES[0] += 1
     return loss, coef
 
 
@@ -371,12 +363,10 @@ def rel_l2_bwd_g(x, y, coef, g):
     dx = torch.empty_like(x)
     check(_lib.lib().b2no_rel_l2_bwd_g(_ptr(x), _ptr(y), _ptr(coef), _ptr(g), _ptr(dx), B, x.numel() // B, _stream()),
           "rel_l2_bwd_g")
-    LAUNCHES[0] += 1
     return dx
 
 
 def gather_segments(flat, ptr_table, offsets, counts, nseg: int):
     check(_lib.lib().b2no_gather_segments(_ptr(flat), _ptr(ptr_table), _ptr(offsets), _ptr(counts), nseg, _stream()),
           "gather_segments")
-    LAUNCHES[0] += 1
 

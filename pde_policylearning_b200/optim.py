@@ -70,7 +70,6 @@ class FusedAdam:
                                     ops._ptr(self.exp_avg_sq), self.bucket.numel, ops._ptr(self.step_counter),
                                     self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
                                     float(grad_scale), ops._stream()), "adam_step")
-        ops.LAUNCHES[0] += 2
 
     def state_dict(self):
         return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_counter,
@@ -111,10 +110,10 @@ class GraphedTrainStep:
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        l0 = ops.LAUNCHES[0]
+        l0 = ops.launch_count()
         with torch.cuda.graph(self.graph):
             self.static_loss = self._eager()
-        self.launches_per_step = ops.LAUNCHES[0] - l0
+        self.launches_per_step = ops.launch_count() - l0
         for dst, src in zip((opt.flat_param, opt.exp_avg, opt.exp_avg_sq, opt.step_counter), saved):
             dst.copy_(src)
 
@@ -134,5 +133,5 @@ class GraphedTrainStep:
         if self.static_tgt.data_ptr() != target.data_ptr():
             self.static_tgt.copy_(target, non_blocking=True)
         self.graph.replay()
-        ops.LAUNCHES[0] += self.launches_per_step
+        ops._REPLAYED[0] += self.launches_per_step
         return self.static_loss
