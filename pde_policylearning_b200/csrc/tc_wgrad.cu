@@ -28,6 +28,7 @@ constexpr int kThreadsWg = 320;  // warps 0-3 converter group A (+ final read-ou
 
 struct WgTc {
   int Co, Cop, Ci, Cip, TP, SUB, nb, S, mblocks;   // TP = pixels per TMA stage, SUB = pixels per MMA chunk (A ring slot)
+  int NS;                                          // A-ring slots (TMEM operand + lo copy): 4 when one M block, else 2
   int tiles_per_img;
   long tiles, tiles_per_cta;
   float* partial;
@@ -44,14 +45,14 @@ __host__ __device__ inline WgLayout wg_layout(const WgTc& p) {
   L.stage_bytes = (L.gbytes + L.xbytes + 1023u) & ~1023u;
   L.lo = L.stage_bytes * p.S;
   L.lo_bytes = ((uint32_t)p.Cip * p.SUB * 4 + 1023u) & ~1023u;     // one slot = the X boxes of one MMA chunk
-  L.dbs = L.lo + 2 * L.lo_bytes;
+  L.dbs = L.lo + (uint32_t)p.NS * L.lo_bytes;
   L.bars = L.dbs + 2u * p.mblocks * 128 * 4;
-  L.total = L.bars + 8 * (2 * p.S + 5) + 16 + 1024;
+  L.total = L.bars + 8 * (2 * p.S + 2 * p.NS + 1) + 16 + 1024;
   return L;
 }
 
-// TMEM columns: A operand ring [buf 0/1][M-block][hi SUB | lo SUB], then the accumulators [M-block][Cip]
-__host__ __device__ inline uint32_t wg_tmem_cols(const WgTc& p) { return 4u * p.SUB * p.mblocks + (uint32_t)p.mblocks * p.Cip; }
+// TMEM columns: A operand ring [slot][M-block][hi SUB | lo SUB], then the accumulators [M-block][Cip]
+__host__ __device__ inline uint32_t wg_tmem_cols(const WgTc& p) { return 2u * p.NS * p.SUB * p.mblocks + (uint32_t)p.mblocks * p.Cip; }
 
 __global__ void __launch_bounds__(kThreadsWg, 1)
 k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUtensorMap tmx, const WgTc p) {
@@ -61,8 +62,8 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
   uint64_t* full = (uint64_t*)(smem + L.bars);
   uint64_t* empty = full + p.S;
   uint64_t* a_full = empty + p.S;
-  uint64_t* a_empty = a_full + 2;
-  uint64_t* done = a_empty + 2;
+  uint64_t* a_empty = a_full + p.NS;
+  uint64_t* done = a_empty + p.NS;
   uint32_t* tslot = (uint32_t*)(done + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NW = p.Cip, TP = p.TP;
@@ -71,7 +72,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
 
   if (tid == 0) {
     for (int s = 0; s < p.S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&a_full[a], 128); mbar_init(&a_empty[a], 1); }
+    for (int a = 0; a < p.NS; a++) { mbar_init(&a_full[a], 128); mbar_init(&a_empty[a], 1); }
     mbar_init(done, 1);
     fence_barrier_init();
   }
@@ -83,7 +84,8 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
   tc_fence_after();
   const uint32_t tbase = *tslot;
   const int SUB = p.SUB, nsub = TP / SUB, nbs = SUB / 32;
-  const uint32_t t_acc = tbase + 4u * SUB * p.mblocks;
+  const uint32_t t_acc = tbase + 2u * p.NS * SUB * p.mblocks;
+  const int NS = p.NS;
   const long t_first = (long)blockIdx.x * p.tiles_per_cta;
   const long t_end = t_first + p.tiles_per_cta < p.tiles ? t_first + p.tiles_per_cta : p.tiles;
 
@@ -118,8 +120,8 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
       const uint32_t ph = (uint32_t)(it / p.S) & 1u;
       mbar_wait(&full[s], ph);
       for (int sub = 0; sub < nsub; sub++, n++) {
-        const int ab = (int)(n & 1);
-        mbar_wait(&a_full[ab], (uint32_t)(n >> 1) & 1u);
+        const int ab = (int)(n % NS);
+        mbar_wait(&a_full[ab], (uint32_t)(n / NS) & 1u);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t st = sbase + (uint32_t)s * L.stage_bytes;
@@ -151,8 +153,8 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
     __syncwarp();
   } else {
     // ===================== converter: X lo in shared memory; G rows -> TMEM A operand (thread = channel row) =====================
-    // two groups of four warps alternate over the sub-chunks (group = A-ring slot), so conversion of chunk n+1 overlaps
-    // the MMAs of chunk n and the conversion latency chain (LDS -> ALU -> tcgen05.st -> wait) is hidden
+    // two groups of four warps alternate over the sub-chunks (chunk n -> group n % 2, ring slot n % NS), so conversion of
+    // chunk n+1 overlaps the MMAs of chunk n; with NS = 4 a group also starts chunk n+2 before the MMAs of chunk n finish
     const int grp = warp >> 2;
     const int ct = tid & 127;
     const int quad = warp & 3;
@@ -167,9 +169,9 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
       mbar_wait(&full[s], ph);
       uint8_t* st = smem + (size_t)s * L.stage_bytes;
       for (int sub = 0; sub < nsub; sub++, n++) {
-        const int ab = (int)(n & 1);
-        if (ab != grp) continue;
-        mbar_wait(&a_empty[ab], ((uint32_t)(n >> 1) & 1u) ^ 1u);     // MMAs of this slot's previous chunk are complete
+        if ((int)(n & 1) != grp) continue;
+        const int ab = (int)(n % NS);
+        mbar_wait(&a_empty[ab], ((uint32_t)(n / NS) & 1u) ^ 1u);     // MMAs of this slot's previous chunk are complete
         tc_fence_after();
         {
           // lo copy of this chunk's X boxes into the slot's lo buffer, elementwise (layout-agnostic)
@@ -211,7 +213,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
               tmem_st16(a0 + (uint32_t)(j * 32), hi); tmem_st16(a0 + (uint32_t)(j * 32 + 16), hi + 16);
               tmem_st16(a0 + (uint32_t)(SUB + j * 32), lo); tmem_st16(a0 + (uint32_t)(SUB + j * 32 + 16), lo + 16);
             }
-          } else if (n < 2) {
+          } else if (n < NS) {
             // pad rows (>= Cop) of an M block: zeroed once per ring slot, never written again
             float z[16];
 #pragma unroll
@@ -279,7 +281,10 @@ int b2no_tc_wgrad(const float* g, const float* x, float* partial, int max_blocks
   B2NO_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   WgLayout L;
   bool ok = false;
+  // two ring slots of 64 px (one M block) / 32 px.  Measured on B200 (cfg2, Co = Ci = 32): four slots of 32 px are SLOWER
+  // (155 us vs 87 us) -- the cost is per chunk hand-over (~0.7 us), not per pixel, so chunks are as large as TMEM allows
   p.SUB = p.mblocks == 1 ? 64 : 32;
+  p.NS = 2;
   if (p.mblocks > 3 || wg_tmem_cols(p) > 512) return 1;
   // bytes in flight decide an HBM-bound kernel: take the largest tile that still leaves >= 4 stages, else the deepest ring
   for (int pass = 0; pass < 2 && !ok; pass++)
