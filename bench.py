@@ -325,17 +325,35 @@ def run_b200(args):
     ms_per_step = ms / args.steps
     value = BATCH * world / (ms_per_step * 1e-3)
 
-    # ---- e2e: pinned host inputs -> H2D -> public API step -> loss.item() (D2H) every step ----
-    def e2e_step():
-        if graphed is not None:
-            return graphed((p_host,), t_host).item()
-        return eager_step(p_host.to(dev, non_blocking=True), t_host.to(dev, non_blocking=True)).item()
+    if args.quick:
+        if rank == 0:
+            emit(json.dumps({"metric": METRIC, "value": round(value, 2), "ms_per_step": round(ms_per_step, 4), "n_gpus": world,
+                             "clocks": clocks, "quick": True}))
+        if world > 1:
+            dist.barrier()
+            if graphed is not None:
+                graphed.close()
+            os._exit(0)
+        return
 
-    for _ in range(2):
-        e2e_step()
-    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    # ---- e2e: pinned host inputs -> H2D -> public API step -> loss.item() (D2H) every step ----
+    # Every step's batch is copied host->device inside the timed region; with the CUDA graph the copy of batch i+1 runs
+    # on a copy stream while step i computes (P.HostBatchPipeline: the public input pipeline), so only the first copy
+    # and the per-step loss read-back sit on the critical path.
+    def e2e_run(steps):
+        if graphed is not None:
+            pipe = P.HostBatchPipeline(graphed)
+            for loss in pipe.run(((p_host,), t_host) for _ in range(steps)):
+                loss.item()
+        else:
+            for _ in range(steps):
+                eager_step(p_host.to(dev, non_blocking=True), t_host.to(dev, non_blocking=True)).item()
+
+    e2e_run(2)
+    ms_e2e = timed(lambda: e2e_run(args.steps), 1) / args.steps
     e2e = {"value": round(BATCH * world / (ms_e2e * 1e-3), 2), "unit": UNIT, "ms_per_step": round(ms_e2e, 4),
-           "h2d_bytes_per_step": p_host.numel() * 4 + t_host.numel() * 4, "d2h_bytes_per_step": 4}
+           "h2d_bytes_per_step": p_host.numel() * 4 + t_host.numel() * 4, "d2h_bytes_per_step": 4,
+           "pipeline": "H2D of batch i+1 overlaps step i (copy stream, two staging sets); loss.item() every step"}
 
     out = None
     if rank == 0:
@@ -386,7 +404,7 @@ def run_b200(args):
         # (seen on 2 GPUs) -- release the graph first, and never let the teardown outlive the result
         dist.barrier()
         if graphed is not None:
-            graphed.graph.reset()
+            graphed.close()
             graphed = None
         torch.cuda.synchronize()
         t = threading.Thread(target=dist.destroy_process_group, daemon=True)
@@ -440,6 +458,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--quick", action="store_true", help="device-timed value only (no e2e, probes or CPU baseline): A/B runs")
     ap.add_argument("--no-graph", action="store_true", help="run the training step eagerly instead of as one CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -14,6 +14,6 @@ from .modules import (  # noqa: F401
     RNO2dObserver, PinoSpectralConv3d, MultiplicativeNet, PINObserver2d,
 )
 from .convert import convert_  # noqa: F401
-from .optim import FusedAdam, GraphedTrainStep  # noqa: F401
+from .optim import FusedAdam, GraphedTrainStep, HostBatchPipeline  # noqa: F401
 
 __version__ = "0.1.0"

@@ -9,7 +9,8 @@ import subprocess
 import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2no.so")
+# B2NO_LIB: load another build of the same sources (A/B measurements of compile-time switches)
+LIB_PATH = os.environ.get("B2NO_LIB") or os.path.join(_HERE, "libb2no.so")
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["plan.cu", "spectral.cu", "pointwise.cu", "tc_pointwise.cu", "tc_wgrad.cu", "tc_mlp.cu", "tc_dft.cu", "optim.cu"]
 
@@ -36,10 +37,10 @@ class Epilogue(C.Structure):
                 ("dact_z", C.c_void_p), ("dact", C.c_int32)]
 
 
-def nvcc_command(out_path: str = LIB_PATH):
+def nvcc_command(out_path: str = LIB_PATH, defines=()):
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     return ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-            "-shared", "-Xcompiler", "-fPIC", "-o", out_path] + srcs
+            "-shared", "-Xcompiler", "-fPIC"] + [f"-D{d}" for d in defines] + ["-o", out_path] + srcs
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -30,9 +30,13 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // suspendTimeHint of mbarrier.try_wait).  Without the hint a waiting warp came back every ~30 ns: in the persistent
 // kernels here a quarter of all issued instructions were TRYWAIT / BRA / YIELD of warps that had nothing to do, taken
 // from the issue slots of the epilogue warps sharing their scheduler.
-constexpr uint32_t kMbarSuspendNs = 20000;
+#ifndef B2NO_MBAR_HINT_NS
+#define B2NO_MBAR_HINT_NS 20000
+#endif
+constexpr uint32_t kMbarSuspendNs = B2NO_MBAR_HINT_NS;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if B2NO_MBAR_HINT_NS > 0
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
@@ -40,6 +44,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendNs)
       : "memory");
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+#endif
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {

@@ -85,7 +85,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
   const uint32_t tbase = *tslot;
   const int SUB = p.SUB, nsub = TP / SUB, nbs = SUB / 32;
   const uint32_t t_acc = tbase + 2u * p.NS * SUB * p.mblocks;
-  const int NS = p.NS;
+  const int NS = p.NS;   // 2 or 3
   const long t_first = (long)blockIdx.x * p.tiles_per_cta;
   const long t_end = t_first + p.tiles_per_cta < p.tiles ? t_first + p.tiles_per_cta : p.tiles;
 
@@ -120,8 +120,9 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
       const uint32_t ph = (uint32_t)(it / p.S) & 1u;
       mbar_wait(&full[s], ph);
       for (int sub = 0; sub < nsub; sub++, n++) {
-        const int ab = (int)(n % NS);
-        mbar_wait(&a_full[ab], (uint32_t)(n / NS) & 1u);
+        const uint32_t un = (uint32_t)n, uq = NS == 3 ? un / 3u : un >> 1;   // 32-bit: a 64-bit division here cost 15 us per launch
+        const int ab = (int)(un - uq * (uint32_t)NS);
+        mbar_wait(&a_full[ab], uq & 1u);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t st = sbase + (uint32_t)s * L.stage_bytes;
@@ -170,8 +171,9 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
       uint8_t* st = smem + (size_t)s * L.stage_bytes;
       for (int sub = 0; sub < nsub; sub++, n++) {
         if ((int)(n & 1) != grp) continue;
-        const int ab = (int)(n % NS);
-        mbar_wait(&a_empty[ab], ((uint32_t)(n / NS) & 1u) ^ 1u);     // MMAs of this slot's previous chunk are complete
+        const uint32_t un = (uint32_t)n, uq = NS == 3 ? un / 3u : un >> 1;
+        const int ab = (int)(un - uq * (uint32_t)NS);
+        mbar_wait(&a_empty[ab], (uq & 1u) ^ 1u);                     // MMAs of this slot's previous chunk are complete
         tc_fence_after();
         {
           // lo copy of this chunk's X boxes into the slot's lo buffer, elementwise (layout-agnostic)
@@ -282,9 +284,11 @@ int b2no_tc_wgrad(const float* g, const float* x, float* partial, int max_blocks
   WgLayout L;
   bool ok = false;
   // two ring slots of 64 px (one M block) / 32 px.  Measured on B200 (cfg2, Co = Ci = 32): four slots of 32 px are SLOWER
-  // (155 us vs 87 us) -- the cost is per chunk hand-over (~0.7 us), not per pixel, so chunks are as large as TMEM allows
+  // (155 us vs 87 us) -- the cost is per chunk hand-over (~0.7 us), not per pixel, so chunks are as large as TMEM allows;
+  // a third 64-px slot (B2NO_WG_SLOTS=3) changes nothing (93.6 vs 93.4 us): the converters do not wait for free slots
   p.SUB = p.mblocks == 1 ? 64 : 32;
-  p.NS = 2;
+  { const char* ns = getenv("B2NO_WG_SLOTS"); p.NS = (p.mblocks == 1 && ns && ns[0] == '3') ? 3 : 2; }
+  if (wg_tmem_cols(p) > 512) p.NS = 2;
   if (p.mblocks > 3 || wg_tmem_cols(p) > 512) return 1;
   // bytes in flight decide an HBM-bound kernel: take the largest tile that still leaves >= 4 stages, else the deepest ring
   for (int pass = 0; pass < 2 && !ok; pass++)

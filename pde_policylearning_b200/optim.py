@@ -135,3 +135,68 @@ class GraphedTrainStep:
         self.graph.replay()
         ops._REPLAYED[0] += self.launches_per_step
         return self.static_loss
+
+    def close(self):
+        """Release the captured graph (call before torch.distributed.destroy_process_group(): destroying the NCCL
+        communicator while a graph that captured its all-reduce is alive blocks)."""
+        if self.graph is not None:
+            self.graph.reset()
+            self.graph = None
+
+
+class HostBatchPipeline:
+    """Feeds pinned HOST batches to a GraphedTrainStep with the host->device copy of batch i+1 running on a copy stream
+    while step i computes (two device staging sets, events both ways).  Every batch is still copied host->device once;
+    only its latency leaves the critical path.
+
+        pipe = HostBatchPipeline(step)
+        for loss in pipe.run(batches):       # batches: iterable of (inputs_tuple, target), pinned host tensors
+            value = loss.item()
+    """
+
+    def __init__(self, step: GraphedTrainStep):
+        self.step = step
+        dev = step.static_tgt.device
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.stage = [([torch.empty_like(t) for t in step.static_in], torch.empty_like(step.static_tgt)) for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]      # staging set filled
+        self.free = [torch.cuda.Event() for _ in range(2)]       # staging set consumed by the step
+
+    def _upload(self, slot, inputs, target, first_use):
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_stream):
+            if not first_use:
+                self.copy_stream.wait_event(self.free[slot])
+            else:
+                self.copy_stream.wait_stream(main)
+            ins, tgt = self.stage[slot]
+            for dst, src in zip(ins, inputs):
+                dst.copy_(src, non_blocking=True)
+            tgt.copy_(target, non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+
+    def run(self, batches):
+        it = iter(batches)
+        try:
+            nxt = next(it)
+        except StopIteration:
+            return
+        main = torch.cuda.current_stream()
+        self._upload(0, nxt[0], nxt[1], True)
+        i = 0
+        while nxt is not None:
+            slot = i & 1
+            try:
+                after = next(it)
+            except StopIteration:
+                after = None
+            if after is not None:
+                self._upload(slot ^ 1, after[0], after[1], i == 0)
+            main.wait_event(self.ready[slot])
+            ins, tgt = self.stage[slot]
+            loss = self.step(tuple(ins), tgt)        # device->device into the graph's static buffers, then replay
+            self.free[slot].record(main)
+            yield loss
+            nxt = after
+            i += 1
+

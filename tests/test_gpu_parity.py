@@ -555,3 +555,63 @@ def test_graphed_train_step_matches_eager():
         assert abs(a - b) < 1e-5 * abs(a), (eager, graphed)
     assert rel(o2.flat_param, o1.flat_param) < 1e-5
     assert int(o2.step_counter.item()) == 3
+
+
+def test_grad_bucket_gather_and_loss_tail():
+    """zero_grad(set_to_none=True) -> backward assigns fresh gradient tensors -> ONE gather kernel fills the flat bucket
+    (unused parameters become zeros, complex gradients as (re, im)); LpLoss tail runs on the device."""
+    import pde_policylearning_b200 as P
+    dev = _dev()
+    torch.manual_seed(41)
+    a = torch.nn.Parameter(torch.randn(5, 3, device=dev))
+    b = torch.nn.Parameter(torch.randn(4, 2, dtype=torch.cfloat, device=dev))
+    c = torch.nn.Parameter(torch.randn(7, device=dev))          # never used: its slot must read zero
+    opt = P.FusedAdam([a, b, c], lr=1e-3)
+    opt.bucket.flat.fill_(123.0)                                # stale content must not survive
+    opt.zero_grad(set_to_none=True)
+    assert a.grad is None and b.grad is None
+    x = torch.randn(6, 5, 3, device=dev)
+    y = torch.randn(6, 4, 2, device=dev)
+    out = torch.cat([(x * a).flatten(1), (y * b).abs().flatten(1)], dim=1)
+    tgt = torch.randn_like(out)
+    loss = P.rel_l2_loss(out, tgt, size_average=True)
+    ref = ((out.double() - tgt.double()).flatten(1).norm(dim=1) / tgt.double().flatten(1).norm(dim=1)).mean()
+    assert abs(loss.item() - ref.item()) < 1e-6 * abs(ref.item())
+    ga, gb = torch.autograd.grad(ref, [a, b], retain_graph=True)
+    loss.backward()
+    opt.sync_grads()
+    flat = opt.bucket.flat
+    o = opt.bucket.offsets
+    assert a.grad.data_ptr() == flat.data_ptr() + 4 * o[0]     # gradients are views of the bucket again
+    assert rel(flat[o[0]:o[0] + 15].reshape(5, 3), ga) < 1e-5
+    assert rel(torch.view_as_complex(flat[o[1]:o[1] + 16].reshape(4, 2, 2)), gb) < 1e-5
+    assert float(flat[o[2]:o[2] + 7].abs().max()) == 0.0
+
+
+def test_host_batch_pipeline_matches_direct_steps():
+    """HostBatchPipeline (H2D of batch i+1 on a copy stream while step i runs) follows the same trajectory as feeding
+    the same pinned batches to the graphed step one by one."""
+    import pde_policylearning_b200 as P
+    dev = _dev()
+
+    def build():
+        torch.manual_seed(51)
+        m = P.FNO2dObserver(6, 6, 8).to(dev)
+        o = P.FusedAdam(m.parameters(), lr=1e-3, weight_decay=1e-4)
+        return m, o
+
+    torch.manual_seed(52)
+    xs = [torch.randn(4, 16, 16, 1).pin_memory() for _ in range(5)]
+    ts = [torch.randn(4, 1, 16, 16).pin_memory() for _ in range(5)]
+    loss_fn = lambda o, t: P.rel_l2_loss(o, t, size_average=False)
+    m1, o1 = build()
+    s1 = P.GraphedTrainStep(m1, loss_fn, o1, (xs[0].to(dev),), ts[0].to(dev))
+    direct = [s1((x,), t).item() for x, t in zip(xs, ts)]
+    m2, o2 = build()
+    s2 = P.GraphedTrainStep(m2, loss_fn, o2, (xs[0].to(dev),), ts[0].to(dev))
+    piped = [l.item() for l in P.HostBatchPipeline(s2).run(((x,), t) for x, t in zip(xs, ts))]
+    for u, v in zip(direct, piped):
+        assert abs(u - v) <= 1e-6 * abs(u), (direct, piped)
+    assert rel(o2.flat_param, o1.flat_param) < 1e-6
+    s1.close()
+    s2.close()
