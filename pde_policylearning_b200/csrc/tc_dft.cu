@@ -35,6 +35,7 @@ constexpr uint32_t kB2Sbo = 32 * kB2Lbo;    // bytes between 8-row groups (128 l
 
 struct FdTc {
   int W, H, R, nk, N1, Kx, Ky, S;
+  int MG;      // 1: the hi*hi and hi*lo products of a K step run as ONE MMA against the stacked [hi; lo] B operand (N = 2 N1)
   long tiles, tiles_per_cta, planes;
   const float* tb; const float* mimg;
   float* spec;
@@ -123,8 +124,13 @@ k_fwd_tc(const __grid_constant__ CUtensorMap tmx, const FdTc p) {
   tc_fence_after();
   const uint32_t tbase = *tslot;
   if (tid == 0) fd_stamp(p, 1);
-  // TMEM columns: [xa: 2 x (32 hi | 32 lo)] [d1: 2 x N1] [mt: H hi | H lo] [d2: 2 x R*N1]
-  const uint32_t t_xa = tbase, t_d1 = tbase + 128u, t_mt = t_d1 + 2u * N1, t_d2 = t_mt + 2u * H;
+  // TMEM columns: [xa: 2 x (32 hi | 32 lo)] [d1: 2 x ND] [mt: H hi | H lo] [d2: 2 x R*ND], ND = N1 or (merged) 2 N1.
+  // A tcgen05.mma of this shape costs ~40 cycles whatever its N (TMEM A-operand fetch), and this kernel's steady state was
+  // exactly its 96 MMAs per tile; the B operands already hold their hi and lo images back to back with one row-group
+  // stride, so A_hi x [B_hi; B_lo] is one instruction with N = 2 N1 and the two accumulator halves are added by the
+  // threads that read them anyway: 64 MMAs per tile.
+  const int ND = p.MG ? 2 * N1 : N1;
+  const uint32_t t_xa = tbase, t_d1 = tbase + 128u, t_mt = t_d1 + 2u * ND, t_d2 = t_mt + 2u * H;
   const long t_first = (long)blockIdx.x * p.tiles_per_cta;
   const long t_end = t_first + p.tiles_per_cta < p.tiles ? t_first + p.tiles_per_cta : p.tiles;
   const int ntiles = (int)(t_end > t_first ? t_end - t_first : 0);
@@ -151,7 +157,7 @@ k_fwd_tc(const __grid_constant__ CUtensorMap tmx, const FdTc p) {
     }
   } else if (warp == 11) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = idesc_tf32(128, N1, 0, 0);
+    const uint32_t idesc = idesc_tf32(128, N1, 0, 0), idesc2 = idesc_tf32(128, 2 * N1, 0, 0);
     const uint32_t sbase = smem_u32(smem);
     const uint32_t sbo1 = (uint32_t)(p.W / 4) * 128;
     const uint64_t d_th = smem_desc(sbase + L.tbh, 128, sbo1, LAYOUT_NONE), d_tl = smem_desc(sbase + L.tbl, 128, sbo1, LAYOUT_NONE);
@@ -164,14 +170,23 @@ k_fwd_tc(const __grid_constant__ CUtensorMap tmx, const FdTc p) {
         if (c == 0) mbar_wait(&d1_empty[db], ((uint32_t)(it >> 1) & 1u) ^ 1u);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t d = t_d1 + (uint32_t)db * N1;
+          const uint32_t d = t_d1 + (uint32_t)(db * ND);
           const uint32_t xa = t_xa + 64u * xb;
-          for (int pass = 0; pass < ((p.debug & 2) ? 0 : 3); pass++) {
-            const uint32_t ac = pass == 1 ? xa + 32 : xa;
-            const uint64_t dt = (pass == 2 ? d_tl : d_th) + (uint64_t)(c * 64);     // 32 K elements = 8 chunks of 128 B
+          if (p.MG) {
+            // x_hi * [T_hi; T_lo] (N = 2 N1), then x_lo * T_hi into the first half
+            const uint64_t dt = d_th + (uint64_t)(c * 64);
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-              mma_tf32_ts(d, ac + 8 * j, dt + (uint64_t)(j * 16), idesc, (c > 0 || pass > 0 || j > 0) ? 1u : 0u);
+            for (int j = 0; j < 4; j++) mma_tf32_ts(d, xa + 8 * j, dt + (uint64_t)(j * 16), idesc2, (c > 0 || j > 0) ? 1u : 0u);
+#pragma unroll
+            for (int j = 0; j < 4; j++) mma_tf32_ts(d, xa + 32 + 8 * j, dt + (uint64_t)(j * 16), idesc, 1u);
+          } else {
+            for (int pass = 0; pass < ((p.debug & 2) ? 0 : 3); pass++) {
+              const uint32_t ac = pass == 1 ? xa + 32 : xa;
+              const uint64_t dt = (pass == 2 ? d_tl : d_th) + (uint64_t)(c * 64);     // 32 K elements = 8 chunks of 128 B
+#pragma unroll
+              for (int j = 0; j < 4; j++)
+                mma_tf32_ts(d, ac + 8 * j, dt + (uint64_t)(j * 16), idesc, (c > 0 || pass > 0 || j > 0) ? 1u : 0u);
+            }
           }
           mma_commit(&xa_empty[xb]);
           if (c == nk - 1) mma_commit(&d1_full[db]);
@@ -187,13 +202,22 @@ k_fwd_tc(const __grid_constant__ CUtensorMap tmx, const FdTc p) {
       if (elect_one()) {
         const uint32_t bh = sbase + L.b2 + (uint32_t)db * 2 * L.b2_bytes, bl = bh + L.b2_bytes;
         for (int r = 0; r < R; r++) {
-          const uint32_t d = t_d2 + (uint32_t)(db * R + r) * N1;
-          for (int pass = 0; pass < 3; pass++) {
-            const uint32_t am = pass == 1 ? t_mt + H : t_mt;
-            const uint32_t bb = (pass == 2 ? bl : bh) + (uint32_t)(r * H / 4) * kB2Lbo;
-            const uint64_t db2 = smem_desc(bb, kB2Lbo, kB2Sbo, LAYOUT_NONE);
+          const uint32_t d = t_d2 + (uint32_t)((db * R + r) * ND);
+          if (p.MG) {
+            // Mt_hi * [A_hi; A_lo] (the lo image follows the hi image at the row-group stride), then Mt_lo * A_hi
+            const uint64_t db2 = smem_desc(bh + (uint32_t)(r * H / 4) * kB2Lbo, kB2Lbo, kB2Sbo, LAYOUT_NONE);
             for (int j = 0; j < H / 8; j++)
-              mma_tf32_ts(d, am + 8 * j, db2 + (uint64_t)(j * (2 * kB2Lbo / 16)), idesc, (pass > 0 || j > 0) ? 1u : 0u);
+              mma_tf32_ts(d, t_mt + 8 * j, db2 + (uint64_t)(j * (2 * kB2Lbo / 16)), idesc2, j > 0 ? 1u : 0u);
+            for (int j = 0; j < H / 8; j++)
+              mma_tf32_ts(d, t_mt + H + 8 * j, db2 + (uint64_t)(j * (2 * kB2Lbo / 16)), idesc, 1u);
+          } else {
+            for (int pass = 0; pass < 3; pass++) {
+              const uint32_t am = pass == 1 ? t_mt + H : t_mt;
+              const uint32_t bb = (pass == 2 ? bl : bh) + (uint32_t)(r * H / 4) * kB2Lbo;
+              const uint64_t db2 = smem_desc(bb, kB2Lbo, kB2Sbo, LAYOUT_NONE);
+              for (int j = 0; j < H / 8; j++)
+                mma_tf32_ts(d, am + 8 * j, db2 + (uint64_t)(j * (2 * kB2Lbo / 16)), idesc, (pass > 0 || j > 0) ? 1u : 0u);
+            }
           }
         }
         mma_commit(&b2_empty[db]);
@@ -274,7 +298,20 @@ k_fwd_tc(const __grid_constant__ CUtensorMap tmx, const FdTc p) {
       float v[32];
 #pragma unroll
       for (int c0 = 0; c0 < 32; c0 += 8)
-        if (c0 < N1) tmem_ld8(t_d1 + lane_base + (uint32_t)(db * N1 + c0), v + c0);
+        if (c0 < N1) tmem_ld8(t_d1 + lane_base + (uint32_t)(db * ND + c0), v + c0);
+      if (p.MG) {
+        tmem_ld_wait();
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 8) {
+          if (c0 < N1) {
+            float u[8];
+            tmem_ld8(t_d1 + lane_base + (uint32_t)(db * ND + N1 + c0), u);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; q++) v[c0 + q] += u[q];
+          }
+        }
+      }
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&d1_empty[db]);
@@ -310,7 +347,20 @@ k_fwd_tc(const __grid_constant__ CUtensorMap tmx, const FdTc p) {
           float v[32];
 #pragma unroll
           for (int c0 = 0; c0 < 32; c0 += 8)
-            if (c0 < N1) tmem_ld8(t_d2 + lane_base + (uint32_t)((db * R + r) * N1 + c0), v + c0);
+            if (c0 < N1) tmem_ld8(t_d2 + lane_base + (uint32_t)((db * R + r) * ND + c0), v + c0);
+          if (p.MG) {
+            tmem_ld_wait();
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 8) {
+              if (c0 < N1) {
+                float u[8];
+                tmem_ld8(t_d2 + lane_base + (uint32_t)((db * R + r) * ND + N1 + c0), u);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 8; q++) v[c0 + q] += u[q];
+              }
+            }
+          }
           tmem_ld_wait();
 #pragma unroll
           for (int q = 0; q < 32; q++)
@@ -325,7 +375,20 @@ k_fwd_tc(const __grid_constant__ CUtensorMap tmx, const FdTc p) {
           float v[32];
 #pragma unroll
           for (int c0 = 0; c0 < 32; c0 += 8)
-            if (c0 < N1) tmem_ld8(t_d2 + lane_base + (uint32_t)((db * R + r) * N1 + c0), v + c0);
+            if (c0 < N1) tmem_ld8(t_d2 + lane_base + (uint32_t)((db * R + r) * ND + c0), v + c0);
+          if (p.MG) {
+            tmem_ld_wait();
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 8) {
+              if (c0 < N1) {
+                float u[8];
+                tmem_ld8(t_d2 + lane_base + (uint32_t)((db * R + r) * ND + N1 + c0), u);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 8; q++) v[c0 + q] += u[q];
+              }
+            }
+          }
           tmem_ld_wait();
           const long plane = tile * R + r;
           if (lane < Kx && plane < p.planes) {
@@ -370,7 +433,11 @@ int b2no_tc_dft_forward(const b2no_plan* plan, int which, const float* x, float*
   p.tiles = (rows + 127) / 128;
   p.tb = tf.tb; p.mimg = tf.mimg; p.spec = spec;
   { const char* dbg = getenv("B2NO_FD_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
-  if (128u + 2u * p.N1 + 2u * p.H + 2u * p.R * p.N1 > 512u) return 1;
+  {
+    const char* mg = getenv("B2NO_FD_MERGE");
+    p.MG = (128u + 4u * p.N1 + 2u * p.H + 4u * p.R * p.N1 <= 512u && !(mg && mg[0] == '0')) ? 1 : 0;
+  }
+  if (!p.MG && 128u + 2u * p.N1 + 2u * p.H + 2u * p.R * p.N1 > 512u) return 1;
   int dev = 0, max_smem = 0;
   B2NO_CHECK_CUDA(cudaGetDevice(&dev));
   B2NO_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));

@@ -54,6 +54,22 @@ __host__ __device__ inline WgLayout wg_layout(const WgTc& p) {
 // TMEM columns: A operand ring [slot][M-block][hi SUB | lo SUB], then the accumulators [M-block][Cip]
 __host__ __device__ inline uint32_t wg_tmem_cols(const WgTc& p) { return 2u * p.NS * p.SUB * p.mblocks + (uint32_t)p.mblocks * p.Cip; }
 
+// debug: %globaltimer stamps of CTA 0 for its first 16 chunks (B2NO_WG_DEBUG & 16), read back with b2no_debug_wg_ts.
+// slot = chunk * 8 + {0 slot free seen, 1 lo copy done, 2 conversion issued, 3 TMEM stores complete, 4 MMA warp saw a_full,
+// 5 MMAs issued + committed, 6 stage full seen (converter), 7 unused}
+// The stamps sit on the hand-over path (every instruction there shows in the launch time), so they are compiled in only
+// with -DB2NO_WG_STAMPS (scripts/wg_ts.py explains how).
+__device__ unsigned long long g_wg_ts[128];
+__device__ __forceinline__ void wg_stamp(const WgTc& p, long n, int what) {
+#ifdef B2NO_WG_STAMPS
+  if ((p.debug & 16) && blockIdx.x == 0 && n < 16) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_wg_ts[n * 8 + what] = t;
+  }
+#endif
+}
+
 __global__ void __launch_bounds__(kThreadsWg, 1)
 k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUtensorMap tmx, const WgTc p) {
   extern __shared__ uint8_t smem_raw[];
@@ -124,6 +140,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
         const int ab = (int)(un - uq * (uint32_t)NS);
         mbar_wait(&a_full[ab], uq & 1u);
         tc_fence_after();
+        if (lane == 0) wg_stamp(p, n, 4);
         if (elect_one()) {
           const uint32_t st = sbase + (uint32_t)s * L.stage_bytes;
           for (int mb = 0; mb < ((p.debug & 4) ? 0 : p.mblocks); mb++) {
@@ -148,6 +165,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
         }
         acc = 1;
         __syncwarp();
+        if (lane == 0) wg_stamp(p, n, 5);
       }
     }
     if (elect_one()) mma_commit(done);
@@ -168,6 +186,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
       const int s = it % p.S;
       const uint32_t ph = (uint32_t)(it / p.S) & 1u;
       mbar_wait(&full[s], ph);
+      if (m == 0 && grp == 0) wg_stamp(p, n, 6);
       uint8_t* st = smem + (size_t)s * L.stage_bytes;
       for (int sub = 0; sub < nsub; sub++, n++) {
         if ((int)(n & 1) != grp) continue;
@@ -175,6 +194,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
         const int ab = (int)(un - uq * (uint32_t)NS);
         mbar_wait(&a_empty[ab], (uq & 1u) ^ 1u);                     // MMAs of this slot's previous chunk are complete
         tc_fence_after();
+        if (m == 0) wg_stamp(p, n, 0);
         {
           // lo copy of this chunk's X boxes into the slot's lo buffer, elementwise (layout-agnostic)
           const uint32_t cnt = (uint32_t)nbs * NW * 128 / 16;
@@ -185,6 +205,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
             dst[i] = make_float4(x.x - tf32_trunc(x.x), x.y - tf32_trunc(x.y), x.z - tf32_trunc(x.z), x.w - tf32_trunc(x.w));
           }
         }
+        if (m == 0) wg_stamp(p, n, 1);
 #pragma unroll
         for (int mb = 0; mb < 3; mb++) {
           if (mb >= ((p.debug & 2) ? 0 : p.mblocks)) break;
@@ -223,9 +244,11 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
             for (int c = 0; c < 2 * SUB; c += 16) tmem_st16(a0 + (uint32_t)c, z);
           }
         }
+        if (m == 0) wg_stamp(p, n, 2);
         tmem_st_wait();
         tc_fence_before();
         fence_proxy_async();
+        if (m == 0) wg_stamp(p, n, 3);
         mbar_arrive(&a_full[ab]);
       }
     }
@@ -267,6 +290,10 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
 }  // namespace
 
 void b2no_tc_count_launch();
+
+extern "C" int b2no_debug_wg_ts(unsigned long long* host128) {
+  return (int)cudaMemcpyFromSymbol(host128, g_wg_ts, sizeof(unsigned long long) * 128);
+}
 
 // Fills `partial` with *nblk per-CTA partials laid out [Co*Ci | Co]; returns 0 on success, 1 if not eligible.
 int b2no_tc_wgrad(const float* g, const float* x, float* partial, int max_blocks, int batch, int ci, int co, long pixels,
