@@ -6,9 +6,9 @@
 //   A = G tile (M = output channels).  Few channels (32) would waste 3/4 of a 128-row shared-memory A read per MMA
 //       (measured: the SS form was shared-memory bound, 1.8 TB/s), so the converter warps (thread = channel row) move
 //       the G tile into TMEM as hi (raw fp32) | lo = rna_tf32(g - trunc g) and the MMAs run in the TS form;
-//   B = X tile straight from the TMA box; its elementwise lo copy lives in a separate two-slot ring (one slot per A-ring
-//       slot) written by the converter warps, so a TMA stage holds nothing but the 2 x TP x channels payload;
-//   D = [Co x Ci] fp32 in TMEM, accumulated over every tile a CTA owns and written once at the end as a per-CTA
+//   B = X tile straight from the TMA box, each box followed by its elementwise lo copy (written by the converter warps
+//       that own no G row), so [X_hi; X_lo] is one B operand of 2 Ci rows;
+//   D = [Co x 2 Ci] fp32 in TMEM (the two halves are added at read-out), accumulated over every tile a CTA owns and written once at the end as a per-CTA
 //       partial; k_pw_wgrad_reduce (pointwise.cu) sums the partials deterministically;
 //   db[o] = sum G[o, .] is summed in registers by the converter thread that owns row o (it reads every G element anyway).
 // 3xTF32: hi*hi + lo*hi + hi*lo.
@@ -35,24 +35,25 @@ struct WgTc {
   int debug;    // ablation (B2NO_WG_DEBUG): 1 no X-lo pass, 2 no G conversion, 4 no MMAs
 };
 
-struct WgLayout { uint32_t gbytes, xbytes, x, stage_bytes, lo, lo_bytes, dbs, bars, total; };
+struct WgLayout { uint32_t gbytes, xbytes, x, stage_bytes, dbs, bars, total; };
 
+// A TMA stage = the G boxes [nb][Cop rows x 128 B] and, per X box, 2 Cip rows: the box itself (hi: the tensor core reads the
+// top 19 bits of the raw fp32) followed by its elementwise lo copy, so that [X_hi; X_lo] is ONE B operand of 2 Cip rows.
 __host__ __device__ inline WgLayout wg_layout(const WgTc& p) {
   WgLayout L;
   L.gbytes = (uint32_t)p.Cop * p.TP * 4;
-  L.xbytes = (uint32_t)p.Cip * p.TP * 4;
+  L.xbytes = 2u * (uint32_t)p.Cip * p.TP * 4;
   L.x = L.gbytes;
   L.stage_bytes = (L.gbytes + L.xbytes + 1023u) & ~1023u;
-  L.lo = L.stage_bytes * p.S;
-  L.lo_bytes = ((uint32_t)p.Cip * p.SUB * 4 + 1023u) & ~1023u;     // one slot = the X boxes of one MMA chunk
-  L.dbs = L.lo + (uint32_t)p.NS * L.lo_bytes;
+  L.dbs = L.stage_bytes * p.S;
   L.bars = L.dbs + 2u * p.mblocks * 128 * 4;
   L.total = L.bars + 8 * (2 * p.S + 2 * p.NS + 1) + 16 + 1024;
   return L;
 }
 
-// TMEM columns: A operand ring [slot][M-block][hi SUB | lo SUB], then the accumulators [M-block][Cip]
-__host__ __device__ inline uint32_t wg_tmem_cols(const WgTc& p) { return 2u * p.NS * p.SUB * p.mblocks + (uint32_t)p.mblocks * p.Cip; }
+// TMEM columns: A operand ring [slot][M-block][hi SUB | lo SUB], then the accumulators [M-block][2 Cip]
+// (columns [0, Cip): G_hi X_hi + G_lo X_hi, columns [Cip, 2 Cip): G_hi X_lo; added at read-out)
+__host__ __device__ inline uint32_t wg_tmem_cols(const WgTc& p) { return 2u * p.NS * p.SUB * p.mblocks + 2u * p.mblocks * p.Cip; }
 
 // debug: %globaltimer stamps of CTA 0 for its first 16 chunks (B2NO_WG_DEBUG & 16), read back with b2no_debug_wg_ts.
 // slot = chunk * 8 + {0 slot free seen, 1 lo copy done, 2 conversion issued, 3 TMEM stores complete, 4 MMA warp saw a_full,
@@ -120,13 +121,15 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
         const int p0 = (int)(tile - (long)b * p.tiles_per_img) * TP;
         for (int j = 0; j < p.nb; j++) {
           tma_load_3d(st + (size_t)j * p.Cop * 128, &tmg, &full[s], p0 + 32 * j, 0, b);
-          tma_load_3d(st + L.x + (size_t)j * NW * 128, &tmx, &full[s], p0 + 32 * j, 0, b);
+          tma_load_3d(st + L.x + (size_t)j * 2 * NW * 128, &tmx, &full[s], p0 + 32 * j, 0, b);
         }
       }
     }
   } else if (warp == 9) {
     // ===================== MMA issuer (TS form: A = G from TMEM, B = X from shared memory) =====================
-    const uint32_t idesc = idesc_tf32(128, NW, 0, 0);
+    // Per K step of 8 px: G_hi x [X_hi; X_lo] as ONE MMA with N = 2 Cip, then G_lo x X_hi (N = Cip) -- an MMA of this shape
+    // costs ~40 cycles whatever its N, and the issue of a chunk's MMAs was the longest item of the hand-over period
+    const uint32_t idesc = idesc_tf32(128, NW, 0, 0), idesc2 = idesc_tf32(128, 2 * NW, 0, 0);
     const uint32_t sbase = smem_u32(smem);
     int it = 0;
     long n = 0;                      // A-ring position (sub-chunk counter)
@@ -144,20 +147,19 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
         if (elect_one()) {
           const uint32_t st = sbase + (uint32_t)s * L.stage_bytes;
           for (int mb = 0; mb < ((p.debug & 4) ? 0 : p.mblocks); mb++) {
-            const uint32_t d = t_acc + (uint32_t)(mb * NW);
+            const uint32_t d = t_acc + (uint32_t)(mb * 2 * NW);
             const uint32_t a0 = tbase + (uint32_t)((ab * p.mblocks + mb) * 2 * SUB);
             uint32_t a2 = acc;
-            for (int pass = 0; pass < 3; pass++) {
-              const uint32_t ga = pass == 1 ? a0 + SUB : a0;
-              const uint32_t xa = pass == 2 ? sbase + L.lo + (uint32_t)ab * L.lo_bytes : st + L.x + (uint32_t)(sub * nbs) * NW * 128;
-              for (int j = 0; j < nbs; j++) {
-                const uint64_t dx = smem_desc(xa + (uint32_t)j * NW * 128, 16, 1024, LAYOUT_SW128);
+            for (int j = 0; j < nbs; j++) {
+              const uint64_t dx = smem_desc(st + L.x + (uint32_t)(sub * nbs + j) * 2 * NW * 128, 16, 1024, LAYOUT_SW128);
 #pragma unroll
-                for (int ks = 0; ks < 4; ks++) {
-                  mma_tf32_ts(d, ga + (uint32_t)(j * 32 + ks * 8), dx + (uint64_t)(ks * 2), idesc, a2);
-                  a2 = 1;
-                }
+              for (int ks = 0; ks < 4; ks++) {
+                mma_tf32_ts(d, a0 + (uint32_t)(j * 32 + ks * 8), dx + (uint64_t)(ks * 2), idesc2, a2);
+                a2 = 1;
               }
+#pragma unroll
+              for (int ks = 0; ks < 4; ks++)
+                mma_tf32_ts(d, a0 + (uint32_t)(SUB + j * 32 + ks * 8), dx + (uint64_t)(ks * 2), idesc, 1u);
             }
           }
           if (sub == nsub - 1) mma_commit(&empty[s]);
@@ -190,21 +192,32 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
       uint8_t* st = smem + (size_t)s * L.stage_bytes;
       for (int sub = 0; sub < nsub; sub++, n++) {
         if ((int)(n & 1) != grp) continue;
+        {
+          // lo copy of this chunk's X boxes, elementwise (layout-agnostic), into the rows right after each box; it needs
+          // no ring slot, so it runs before the slot wait -- and on the warps that own no real G row when there are such
+          // (Co <= 96: the quad-0 warp converts while the other three copy)
+          const int first_idle = (p.mblocks == 1) ? ((p.Cop + 31) >> 5) : 4;      // quads >= first_idle hold only pad rows
+          const int nidle = 4 - first_idle;
+          const bool copier = nidle == 0 || quad >= first_idle;
+          if (copier && !(p.debug & 1)) {
+            const int cthreads = nidle == 0 ? 128 : nidle * 32;
+            const int cid = nidle == 0 ? ct : (quad - first_idle) * 32 + lane;
+            const uint32_t per_box = (uint32_t)NW * 128 / 16;
+            for (int j = 0; j < nbs; j++) {
+              const float4* src = (const float4*)(st + L.x + (size_t)(sub * nbs + j) * 2 * NW * 128);
+              float4* dst = (float4*)((uint8_t*)src + (size_t)NW * 128);
+              for (uint32_t i = cid; i < per_box; i += cthreads) {
+                const float4 x = src[i];
+                dst[i] = make_float4(x.x - tf32_trunc(x.x), x.y - tf32_trunc(x.y), x.z - tf32_trunc(x.z), x.w - tf32_trunc(x.w));
+              }
+            }
+          }
+        }
         const uint32_t un = (uint32_t)n, uq = NS == 3 ? un / 3u : un >> 1;
         const int ab = (int)(un - uq * (uint32_t)NS);
         mbar_wait(&a_empty[ab], (uq & 1u) ^ 1u);                     // MMAs of this slot's previous chunk are complete
         tc_fence_after();
         if (m == 0) wg_stamp(p, n, 0);
-        {
-          // lo copy of this chunk's X boxes into the slot's lo buffer, elementwise (layout-agnostic)
-          const uint32_t cnt = (uint32_t)nbs * NW * 128 / 16;
-          const float4* src = (const float4*)(st + L.x + (size_t)(sub * nbs) * NW * 128);
-          float4* dst = (float4*)(smem + L.lo + (size_t)ab * L.lo_bytes);
-          for (uint32_t i = ct; i < ((p.debug & 1) ? 0u : cnt); i += 128) {
-            const float4 x = src[i];
-            dst[i] = make_float4(x.x - tf32_trunc(x.x), x.y - tf32_trunc(x.y), x.z - tf32_trunc(x.z), x.w - tf32_trunc(x.w));
-          }
-        }
         if (m == 0) wg_stamp(p, n, 1);
 #pragma unroll
         for (int mb = 0; mb < 3; mb++) {
@@ -267,9 +280,12 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
       for (int mb = 0; mb < p.mblocks; mb++) {
         const int o = mb * 128 + m;
         for (int c0 = 0; c0 < NW; c0 += 16) {
-          float v[16];
-          tmem_ld16(t_acc + lane_base + (uint32_t)(mb * NW + c0), v);
+          float v[16], u[16];
+          tmem_ld16(t_acc + lane_base + (uint32_t)(mb * 2 * NW + c0), v);
+          tmem_ld16(t_acc + lane_base + (uint32_t)(mb * 2 * NW + NW + c0), u);
           tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; j++) v[j] += u[j];
           if (o < p.Co) {
 #pragma unroll
             for (int j = 0; j < 16; j++) {
