@@ -191,8 +191,8 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
       if (m == 0 && grp == 0) wg_stamp(p, n, 6);
       uint8_t* st = smem + (size_t)s * L.stage_bytes;
       for (int sub = 0; sub < nsub; sub++, n++) {
-        // (measured: letting BOTH groups convert every chunk, one box each, is slower -- 96 vs 80 us: every chunk then
-        // synchronises all eight warps)
+        // (measured and rejected: BOTH groups converting every chunk, one box each: 96 vs 80 us -- every chunk then
+        // synchronises all eight warps; G rows loaded into registers ahead of the slot wait: 90 vs 80 us)
         if ((int)(n & 1) != grp) continue;
         {
           // lo copy of this chunk's X boxes, elementwise (layout-agnostic), into the rows right after each box; it needs
