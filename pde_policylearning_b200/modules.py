@@ -452,12 +452,11 @@ class FNO2dObserver(nn.Module):
         return g
 
     def forward(self, p_plane, v_plane=None):
+        # fno_models.py:41-57 concatenates channels-LAST and permutes; the lifting kernel wants channels-first, so the
+        # concatenation writes that layout directly (one copy kernel instead of cat + permute copy; same values)
         grid = self.get_grid(p_plane.shape, p_plane.device)
-        if self.use_v_plane:
-            p_plane = torch.cat((p_plane, v_plane, grid), dim=-1)
-        else:
-            p_plane = torch.cat((p_plane, grid), dim=-1)
-        return self.fno2d(p_plane.permute(0, 3, 1, 2))
+        parts = [p_plane, v_plane, grid] if self.use_v_plane else [p_plane, grid]
+        return self.fno2d(torch.cat([t.permute(0, 3, 1, 2) for t in parts], dim=1))
 
 
 class LpLoss(object):

@@ -175,6 +175,26 @@ class HostBatchPipeline:
             tgt.copy_(target, non_blocking=True)
             self.ready[slot].record(self.copy_stream)
 
+    def run_losses(self, batches):
+        """Like run(), but yields the loss of every step as a Python float read back through a pinned host buffer ONE
+        STEP LATE: the 4-byte device->host copy of step i is enqueued right after its replay and awaited only after step
+        i+1 has been launched, so the GPU never idles on the host's read-back (every step's loss is still read)."""
+        dev = self.step.static_tgt.device
+        host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        main = torch.cuda.current_stream(dev)
+        i = 0
+        for loss in self.run(batches):
+            host[i & 1].copy_(loss, non_blocking=True)
+            done[i & 1].record(main)
+            if i > 0:
+                done[(i - 1) & 1].synchronize()
+                yield float(host[(i - 1) & 1])
+            i += 1
+        if i > 0:
+            done[(i - 1) & 1].synchronize()
+            yield float(host[(i - 1) & 1])
+
     def run(self, batches):
         it = iter(batches)
         try:

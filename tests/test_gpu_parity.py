@@ -613,5 +613,13 @@ def test_host_batch_pipeline_matches_direct_steps():
     for u, v in zip(direct, piped):
         assert abs(u - v) <= 1e-6 * abs(u), (direct, piped)
     assert rel(o2.flat_param, o1.flat_param) < 1e-6
+    # deferred read-back: same losses, every step delivered
+    m3, o3 = build()
+    s3 = P.GraphedTrainStep(m3, loss_fn, o3, (xs[0].to(dev),), ts[0].to(dev))
+    late = list(P.HostBatchPipeline(s3).run_losses(((x,), t) for x, t in zip(xs, ts)))
+    assert len(late) == len(direct)
+    for u, v in zip(direct, late):
+        assert abs(u - v) <= 1e-6 * abs(u), (direct, late)
     s1.close()
     s2.close()
+    s3.close()
