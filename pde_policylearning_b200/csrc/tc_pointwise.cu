@@ -159,7 +159,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const uint32_t bytes = xb1 + xb2 + 2 * ab + ((MODE == 3) ? (uint32_t)p.Cz * 512 : 0u);
+      const uint32_t bytes = xb1 + xb2 + ab + ((MODE == 3) ? (uint32_t)p.Cz * 512 : 0u);
       int it = 0;
       for (long tile = t_first; tile < t_end; tile++, it++) {
         const int s = it % p.S;
@@ -174,8 +174,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
         if (MODE == 3 && p.Cz) tma_load_3d(st + L.dz, &tm3, &full[s], t_in_img * 128, 0, b);
         if (p.Ks) {
           const size_t off = (size_t)tile * p.R * p.Qp * p.Np;
-          bulk_load(st + L.ah, p.ahi + off, ab, &full[s]);
-          bulk_load(st + L.al, p.alo + off, ab, &full[s]);
+          bulk_load(st + L.ah, p.ahi + off, ab, &full[s]);     // fp32 image; the converter warps split it into hi | lo
         }
       }
     }
@@ -266,6 +265,19 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
       const int a = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
       mbar_wait(&full[s], ph);
+      if (p.Ks) {
+        // A' rows arrive as ONE fp32 image (half the bytes k_inv_h writes and this kernel reads); split it in place into
+        // the tf32 hi image and the lo image next to it, then make the generic-proxy writes visible to the MMAs
+        float* ah = (float*)(smem + L.stages + (size_t)s * L.stage_bytes + L.ah);
+        float* al = (float*)(smem + L.stages + (size_t)s * L.stage_bytes + L.al);
+        for (int i = m * 4; i < p.Ks * p.Np; i += 512) {
+          const float4 v = *reinterpret_cast<const float4*>(ah + i);
+          const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+          *reinterpret_cast<float4*>(ah + i) = h;
+          *reinterpret_cast<float4*>(al + i) = make_float4(tf32_rna(v.x - h.x), tf32_rna(v.y - h.y), tf32_rna(v.z - h.z), tf32_rna(v.w - h.w));
+        }
+        fence_proxy_async();
+      }
       mbar_wait(&a_empty[a], aph ^ 1u);
       tc_fence_after();
       const float* sx = (const float*)(smem + L.stages + (size_t)s * L.stage_bytes);
@@ -416,7 +428,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
   if (warp == 1) tmem_dealloc(tbase, ncols);
 }
 
-// A'[b][row][q/4][n/8][n%8][q%4] (hi and lo) from the kept spectrum: the second-to-last inverse stage.
+// A'[b][row][q/4][n/8][n%8][q%4] (one fp32 image) from the kept spectrum: the second-to-last inverse stage.
 //   S[b,o,h,ky] = sum_kx M[kx][h] * spec[b][o][kx][ky];   q = 2 ky -> Re S, 2 ky + 1 -> Im S
 // One block per (sample, group of HB rows): the sample's spectrum is staged in shared memory once.
 constexpr int kInvHB = 32;
@@ -464,9 +476,7 @@ k_inv_h(const float2* __restrict__ spec, const float2* __restrict__ M, float* __
         }
       }
       const size_t off = off0 + (size_t)hl * Qp * Np;
-      const float hr = tf32_rna(sr), hi = tf32_rna(si);
-      *reinterpret_cast<float2*>(ahi + off) = make_float2(hr, hi);
-      *reinterpret_cast<float2*>(alo + off) = make_float2(tf32_rna(sr - hr), tf32_rna(si - hi));
+      *reinterpret_cast<float2*>(ahi + off) = make_float2(sr, si);   // fp32; k_pw_tc's converter warps make the hi / lo split
     }
   }
 }
