@@ -455,8 +455,14 @@ class FNO2dObserver(nn.Module):
         # fno_models.py:41-57 concatenates channels-LAST and permutes; the lifting kernel wants channels-first, so the
         # concatenation writes that layout directly (one copy kernel instead of cat + permute copy; same values)
         grid = self.get_grid(p_plane.shape, p_plane.device)
-        parts = [p_plane, v_plane, grid] if self.use_v_plane else [p_plane, grid]
-        return self.fno2d(torch.cat([t.permute(0, 3, 1, 2) for t in parts], dim=1))
+        cf = self._grid_cache.get("cf")
+        if cf is None or cf[0] is not grid:
+            cf = (grid, grid.permute(0, 3, 1, 2).contiguous())     # the constant grid channels, channels-first, made once
+            self._grid_cache["cf"] = cf
+        parts = [p_plane, v_plane] if self.use_v_plane else [p_plane]
+        # (B, H, W, 1) -> (B, 1, H, W) is a pure reshape
+        cfirst = [t.reshape(t.shape[0], 1, t.shape[1], t.shape[2]) if t.shape[-1] == 1 else t.permute(0, 3, 1, 2) for t in parts]
+        return self.fno2d(torch.cat(cfirst + [cf[1]], dim=1))
 
 
 class LpLoss(object):
