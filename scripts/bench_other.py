@@ -42,6 +42,14 @@ try:
     ms = timed(rno_step)
     print(f"cfg3 RNO2dObserver(12,12,34,L=1) B={rno_B} T={rno_T} 32x32 fwd+bwd eager: {ms:.1f} ms/step = "
           f"{rno_B / ms * 1e3:.1f} trajectories/s at T={rno_T} ({ms / rno_T:.2f} ms per recurrent step)")
+    # the same step (plus fused Adam) captured once into a CUDA graph: what is left when the host launch loop is gone
+    opt = P.FusedAdam(m.parameters(), lr=1e-3)
+    lf = lambda o, t: P.rel_l2_loss(o.reshape(rno_B, -1), t.reshape(rno_B, -1), size_average=False)
+    gstep = P.GraphedTrainStep(m, lf, opt, (x,), tgt, warmup=2)
+    ms = timed(lambda: gstep((x,), tgt))
+    print(f"cfg3 same, fwd + loss + bwd + Adam as ONE CUDA graph ({gstep.launches_per_step} library launches): {ms:.1f} ms/step = "
+          f"{rno_B / ms * 1e3:.1f} trajectories/s at T={rno_T} ({ms / rno_T:.2f} ms per recurrent step)")
+    gstep.close()
 except Exception as e:  # noqa: BLE001
     print("cfg3 failed:", type(e).__name__, e)
 
