@@ -13,6 +13,7 @@ from .modules import (  # noqa: F401
     RnoSpectralConv2d, FourierLayer2d, RNO_cell, RNO_layer, SpectralConvWithFC, SpectralRegressor, RNO2d,
     RNO2dObserver, PinoSpectralConv3d, MultiplicativeNet, PINObserver2d,
 )
+from .pino_loss import channelflow_pino_loss, fdm_ns_vorticity, get_forcing  # noqa: F401
 from .convert import convert_  # noqa: F401
 from .optim import FusedAdam, GraphedTrainStep, HostBatchPipeline  # noqa: F401
 

@@ -295,12 +295,21 @@ def test_golden_pinobserver(golden):
     m = P.PINObserver2d(modes1=[3] * 3, modes2=[3] * 3, modes3=[3] * 3, fc_dim=16, layers=[8] * 4, act="gelu",
                         pad_ratio=0.0625)
     u, re = c["u"].to(dev), c["inputs"][1].to(dev)
-    forcing = rs.get_forcing(8).to(dev)
+    forcing = P.get_forcing(8, device=dev)
+    assert torch.equal(forcing.cpu(), c["forcing"])
 
     def loss_fn(o):
+        # the product's PINO loss (pino_loss.py: DFT-matrix contractions, no torch.fft) against the reference's fixtures
         data = P.rel_l2_loss(o.reshape(2, 8, 8, 17), u, True)
-        lic, lf = rs.channelflow_pino_loss(o, u[..., 0], forcing, 1 / re, c["t_interval"])
+        lic, lf = P.channelflow_pino_loss(o, u[..., 0], forcing, 1 / re, c["t_interval"])
         return 5.0 * data + lf + lic
+
+    with torch.no_grad():
+        ref_out = c["out"].to(dev)
+        lic, lf = P.channelflow_pino_loss(ref_out, u[..., 0], forcing, 1 / re, c["t_interval"])
+        assert abs(lic.item() - c["loss_ic"].item()) <= 1e-5 * abs(c["loss_ic"].item())
+        assert abs(lf.item() - c["loss_f"].item()) <= 1e-5 * abs(c["loss_f"].item())
+        assert rel(P.fdm_ns_vorticity(ref_out.reshape(2, 8, 8, 17), 1 / re, c["t_interval"]), c["Du"]) < TOL
 
     _run_model(m, c, dev, loss_fn, gtol=2e-4)
     # inference path (fused head) gives the same output

@@ -147,3 +147,29 @@ def test_fast_erf_coefficients():
     approx = (x * p / q).astype(np.float64)
     ref = torch.erf(torch.linspace(-6, 6, 400001, dtype=torch.float64)).numpy()
     assert np.abs(approx - ref).max() < 6e-7
+
+
+def test_pino_residual_matches_reference_fixture_and_oracle(golden):
+    """Row a8 (diff_control_env.py:5-41) as DFT-matrix contractions: the residual of the reference's own output equals
+    the Du the unmodified reference produced (fixture), and values + gradients equal the torch.fft restatement."""
+    import pde_policylearning_b200 as P
+    from oracle import restated as rs
+    c = golden("a7_pinobserver2d")
+    re = c["inputs"][1]
+    du = P.fdm_ns_vorticity(c["out"].reshape(2, 8, 8, 17), 1 / re, c["t_interval"])
+    assert float((du - c["Du"]).norm() / c["Du"].norm()) < 1e-5
+    assert torch.equal(P.get_forcing(8), c["forcing"])
+    torch.manual_seed(3)
+    for n, t in ((16, 6), (64, 5)):
+        w = torch.randn(2, n, n, t, dtype=torch.float64, requires_grad=True)
+        v = torch.rand(2, dtype=torch.float64) * 0.01 + 0.002
+        a = P.fdm_ns_vorticity(w, v, 0.5)
+        b = rs.fdm_ns_vorticity(w, v, 0.5)
+        assert float((a - b).norm() / b.norm()) < 1e-12
+        g = torch.randn_like(a)
+        (ga,) = torch.autograd.grad(a, w, g, retain_graph=True)
+        (gb,) = torch.autograd.grad(b, w, g)
+        assert float((ga - gb).norm() / gb.norm()) < 1e-12
+    with pytest.raises(ValueError):
+        P.fdm_ns_vorticity(torch.randn(1, 7, 7, 4), torch.ones(1), 1.0)
+
