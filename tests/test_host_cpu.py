@@ -173,3 +173,21 @@ def test_pino_residual_matches_reference_fixture_and_oracle(golden):
     with pytest.raises(ValueError):
         P.fdm_ns_vorticity(torch.randn(1, 7, 7, 4), torch.ones(1), 1.0)
 
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference: ONE JSON line on stdout with the contract's keys (the CPU arm runs without a GPU)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "fno2d_fwd_bwd_samples_per_s" and d["unit"] == "samples/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"]
