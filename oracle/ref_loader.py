@@ -189,6 +189,7 @@ def load():
         PinoSpectralConv3d=basics.SpectralConv3d, PinoSpectralConv2d=basics.SpectralConv2d,
         PinoSpectralConv1d=basics.SpectralConv1d,
         PINObserver2d=pinobs.PINObserver2d, MultiplicativeNet=pinobs.MultiplicativeNet,
+        PINObserverFullField=pinobs.PINObserverFullField, PolicyModel2D=pinobs.PolicyModel2D,
         LpLoss=losses.LpLoss, get_forcing=losses.get_forcing,
         Channelflow_PINO_loss=dce.Channelflow_PINO_loss, FDM_NS_vorticity=dce.FDM_NS_vorticity,
     )

@@ -227,9 +227,12 @@ def _mult_net(sd, pre, t, re):
     return t @ sd[pre + "B"].to(dt).t() + code[:, None, None, None, :] + sd[pre + "bias"].to(dt)
 
 
-def pinobserver2d_forward(sd, x, re, modes1, modes2, modes3, layers, pad_ratio=0.0625, act=F.gelu):
-    """pinobserver.py:192-233."""
+def pinobserver2d_forward(sd, x, re, modes1, modes2, modes3, layers, pad_ratio=0.0625, act=F.gelu, head="", re_scale=1.0):
+    """pinobserver.py:192-233.  head / re_scale: the same trunk as used by PINObserverFullField (:341-368: parameters of
+    the Fourier stack and the tail live under `observer_head.`, re / max_re with max_re = 1000 :313,350) and PolicyModel2D
+    (:436-463: under `pred_net.`, same re scaling); fc0 and the two MultiplicativeNets stay at the top level."""
     dt = x.dtype
+    re = re.float() / re_scale if re_scale != 1.0 else re
     if isinstance(pad_ratio, float):
         pad_ratio = [pad_ratio, pad_ratio]
     size_z = x.shape[-2]
@@ -242,10 +245,10 @@ def pinobserver2d_forward(sd, x, re, modes1, modes2, modes3, layers, pad_ratio=0
     if max(num_pad) > 0:
         t = F.pad(t, (num_pad[0], num_pad[1]), "constant", 0)
     for i in range(L):
-        ws = [sd[f"sp_convs.{i}.weights{j}"] for j in (1, 2, 3, 4)]
+        ws = [sd[f"{head}sp_convs.{i}.weights{j}"] for j in (1, 2, 3, 4)]
         x1 = pino_spectral_conv3d(t, *ws, modes1[i], modes2[i], modes3[i])
-        w = sd[f"ws.{i}.weight"].to(dt)[:, :, 0]
-        x2 = torch.einsum("oi,bixyz->boxyz", w, t) + sd[f"ws.{i}.bias"].to(dt).reshape(1, -1, 1, 1, 1)
+        w = sd[f"{head}ws.{i}.weight"].to(dt)[:, :, 0]
+        x2 = torch.einsum("oi,bixyz->boxyz", w, t) + sd[f"{head}ws.{i}.bias"].to(dt).reshape(1, -1, 1, 1, 1)
         t = x1 + x2
         if i != L - 1:
             t = act(t)
@@ -253,8 +256,20 @@ def pinobserver2d_forward(sd, x, re, modes1, modes2, modes3, layers, pad_ratio=0
         t = t[..., num_pad[0]:-num_pad[1]]
     t = t.permute(0, 2, 3, 4, 1)
     t = _mult_net(sd, "multiplicative_net2.", t, re.float())
-    t = act(t @ sd["fc1.weight"].to(dt).t() + sd["fc1.bias"].to(dt))
-    return t @ sd["fc2.weight"].to(dt).t() + sd["fc2.bias"].to(dt)
+    t = act(t @ sd[f"{head}fc1.weight"].to(dt).t() + sd[f"{head}fc1.bias"].to(dt))
+    return t @ sd[f"{head}fc2.weight"].to(dt).t() + sd[f"{head}fc2.bias"].to(dt)
+
+
+def pinobserver_fullfield_forward(sd, x, re, modes1, modes2, modes3, layers, pad_ratio=0.0625, act=F.gelu):
+    """PINObserverFullField.forward, pinobserver.py:341-368: one shared trunk whose tail emits out_dim * plane_num channels,
+    returned planes-first (b, p, x, y, t)."""
+    out = pinobserver2d_forward(sd, x, re, modes1, modes2, modes3, layers, pad_ratio, act, head="observer_head.", re_scale=1000.0)
+    return out.permute(0, 4, 1, 2, 3)
+
+
+def policy_model2d_forward(sd, x, re, modes1, modes2, modes3, layers, pad_ratio=0.0625, act=F.gelu):
+    """PolicyModel2D.forward, pinobserver.py:436-463 (the constructor zero-initialises every parameter, :432-433)."""
+    return pinobserver2d_forward(sd, x, re, modes1, modes2, modes3, layers, pad_ratio, act, head="pred_net.", re_scale=1000.0)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -158,7 +158,29 @@ def main():
     d["Du"] = ref.FDM_NS_vorticity(o.reshape(2, 8, 8, 17), 1 / re, 0.5).detach()
     out["a7_pinobserver2d"] = d
 
+    # ---- 8f rank 4: the other consumers of the PINO trunk (pinobserver.py:276-463) ----------------
+    torch.manual_seed(1240)
+    ff = ref.PINObserverFullField(plane_num=3, modes1=[3] * 3, modes2=[3] * 3, modes3=[3] * 3, fc_dim=16, layers=[8] * 4,
+                                  act="gelu", pad_ratio=0.0625)
+    a = torch.randn(2, 8, 8, 9, 4)
+    re = torch.tensor([180.0, 420.0])
+    out["a10_pinobserver_fullfield"] = model_case(ff, [a, re], None, dict(plane_num=3))
+    pol = ref.PolicyModel2D(modes1=[3] * 3, modes2=[3] * 3, modes3=[3] * 3, fc_dim=16, layers=[8] * 4, act="gelu",
+                            pad_ratio=0.0625)
+    d0 = model_case(pol, [a, re], None, {})           # as constructed: every parameter zero (pinobserver.py:432-433)
+    assert float(d0["out"].abs().max()) == 0.0
+    with torch.no_grad():
+        for prm in pol.parameters():                   # a trained policy: random parameters of the reference's init scale
+            if prm.is_complex():
+                prm.copy_(torch.view_as_complex(torch.rand(*prm.shape, 2)) / 64.0)
+            else:
+                prm.copy_(torch.randn_like(prm) * 0.2)
+    out["a11_policy_model2d"] = model_case(pol, [a, re], None, {})
+
+    only = os.environ.get("GOLDEN_ONLY")               # e.g. GOLDEN_ONLY=a10,a11: write just the new fixtures
     for k, v in out.items():
+        if only and not any(k.startswith(p) for p in only.split(",")):
+            continue
         path = os.path.join(HERE, k + ".pt")
         torch.save(v, path)
         print(k, os.path.getsize(path) // 1024, "KiB")

@@ -124,3 +124,21 @@ def test_restated_pino(golden):
     # same input as the reference used (the residual amplifies 1e-7 input noise through d/dt and the Laplacian)
     Du = rs.fdm_ns_vorticity(c["out"].reshape(2, 8, 8, 17), 1 / re, c["t_interval"])
     assert cf.rel_l2(Du, c["Du"]) < 5e-6
+
+
+def test_restated_pino_fullfield_and_policy(golden):
+    """the other consumers of the PINO trunk (pinobserver.py:276-463), fixtures from the unmodified
+    reference -- output AND every parameter gradient of the restatement."""
+    for name, fwd in (("a10_pinobserver_fullfield", rs.pinobserver_fullfield_forward),
+                      ("a11_policy_model2d", rs.policy_model2d_forward)):
+        c = golden(name)
+        a, re = c["inputs"]
+        sd = {k: v.clone().requires_grad_(True) for k, v in c["state_dict"].items()}
+        out = fwd(sd, a, re, [3] * 3, [3] * 3, [3] * 3, [8] * 4)
+        assert out.shape == c["out"].shape
+        assert cf.rel_l2(out, c["out"]) < 5e-6, name
+        names = list(c["grads"].keys())
+        gs = torch.autograd.grad(out.square().mean(), [sd[n] for n in names])
+        for n, g in zip(names, gs):
+            assert cf.rel_l2(g, c["grads"][n]) < 5e-5, (name, n)      # fp32 round-off of two op orders on 1e-9-sized gradients
+    assert golden("a10_pinobserver_fullfield")["out"].shape == (2, 3, 8, 8, 9)      # planes first (pinobserver.py:360)
