@@ -167,6 +167,7 @@ def load():
         net = types.ModuleType("libs.DINo.network"); net.MultiplicativeNet = object
         sys.modules["libs.DINo"] = dn; sys.modules["libs.DINo.network"] = net
         pinobs = importlib.import_module("libs.models.pino_models.pinobserver")
+    f2d = importlib.import_module("libs.models.pino_models.fourier2d")
     pu = types.ModuleType("libs.pino_utils"); pu.__path__ = [os.path.join(REFERENCE_ROOT, "libs/pino_utils")]
     sys.modules.setdefault("libs.pino_utils", pu)
     losses = importlib.import_module("libs.pino_utils.losses")
@@ -190,6 +191,7 @@ def load():
         PinoSpectralConv1d=basics.SpectralConv1d,
         PINObserver2d=pinobs.PINObserver2d, MultiplicativeNet=pinobs.MultiplicativeNet,
         PINObserverFullField=pinobs.PINObserverFullField, PolicyModel2D=pinobs.PolicyModel2D,
+        PinoFNO2d=f2d.FNO2d,
         LpLoss=losses.LpLoss, get_forcing=losses.get_forcing,
         Channelflow_PINO_loss=dce.Channelflow_PINO_loss, FDM_NS_vorticity=dce.FDM_NS_vorticity,
     )

@@ -218,6 +218,48 @@ def pino_spectral_conv3d(x, w1, w2, w3, w4, m1, m2, m3):
     return torch.fft.irfftn(out, s=(x.size(2), x.size(3), x.size(4)), dim=[2, 3, 4])
 
 
+def pino_spectral_conv2d(x, w1, w2, m1, m2):
+    """basics.py:79-96: rfftn (norm 'backward'), weights1 on rows [0, m1), weights2 on rows [-m1, N), columns [0, m2),
+    modes un-halved; the high corner is assigned last (overwrites on overlap)."""
+    cdt = torch.complex128 if x.dtype == torch.float64 else torch.complex64
+    B, Co = x.shape[0], w1.shape[1]
+    xf = torch.fft.rfftn(x, dim=[2, 3])
+    out = torch.zeros(B, Co, x.size(-2), x.size(-1) // 2 + 1, dtype=cdt)
+    out[:, :, :m1, :m2] = torch.einsum("bixy,ioxy->boxy", xf[:, :, :m1, :m2], w1.to(cdt))
+    out[:, :, -m1:, :m2] = torch.einsum("bixy,ioxy->boxy", xf[:, :, -m1:, :m2], w2.to(cdt))
+    return torch.fft.irfftn(out, s=(x.size(-2), x.size(-1)), dim=[2, 3])
+
+
+def pino_fno2d_forward(sd, x, modes1, modes2, layers, pad_ratio=(0.0, 0.0), act=F.gelu):
+    """libs/models/pino_models/fourier2d.py:54-87: fc0, [SpectralConv2d + Conv1d(k=1)] stack with the activation after
+    every layer but the last, optional zero padding of both grid dims (:61-65,:71,:80), three-layer tail fc1-act-fc2-act-fc3."""
+    dt = x.dtype
+    if isinstance(pad_ratio, float):
+        pad_ratio = [pad_ratio, pad_ratio]
+    s1, s2 = x.shape[1], x.shape[2]
+    padded = max(pad_ratio) > 0
+    np1 = [round(r * s1) for r in pad_ratio] if padded else [0, 0]
+    np2 = [round(r * s2) for r in pad_ratio] if padded else [0, 0]
+    L = len(layers) - 1
+    t = x @ sd["fc0.weight"].to(dt).t() + sd["fc0.bias"].to(dt)
+    t = t.permute(0, 3, 1, 2)
+    if max(np1) > 0 or max(np2) > 0:
+        t = F.pad(t, (np2[0], np2[1], np1[0], np1[1]), "constant", 0.0)
+    for i in range(L):
+        x1 = pino_spectral_conv2d(t, sd[f"sp_convs.{i}.weights1"], sd[f"sp_convs.{i}.weights2"], modes1[i], modes2[i])
+        w = sd[f"ws.{i}.weight"].to(dt)[:, :, 0]
+        x2 = torch.einsum("oi,bixy->boxy", w, t) + sd[f"ws.{i}.bias"].to(dt).reshape(1, -1, 1, 1)
+        t = x1 + x2
+        if i != L - 1:
+            t = act(t)
+    if max(np1) > 0 or max(np2) > 0:
+        t = t[..., np1[0]:t.shape[-2] - np1[1], np2[0]:t.shape[-1] - np2[1]]
+    t = t.permute(0, 2, 3, 1)
+    t = act(t @ sd["fc1.weight"].to(dt).t() + sd["fc1.bias"].to(dt))
+    t = act(t @ sd["fc2.weight"].to(dt).t() + sd["fc2.bias"].to(dt))
+    return t @ sd["fc3.weight"].to(dt).t() + sd["fc3.bias"].to(dt)
+
+
 def _mult_net(sd, pre, t, re):
     """pinobserver.py:41-59: input1 @ B^T + re @ A^T + bias (affine)."""
     dt = t.dtype

@@ -177,6 +177,14 @@ def main():
                 prm.copy_(torch.randn_like(prm) * 0.2)
     out["a11_policy_model2d"] = model_case(pol, [a, re], None, {})
 
+    # ---- 8f rank 4: libs/models/pino_models/fourier2d.FNO2d (basics.SpectralConv2d, two-sided padding) -----
+    torch.manual_seed(1241)
+    f2 = ref.PinoFNO2d(modes1=[4] * 3, modes2=[3] * 3, fc_dim=12, layers=[6, 8, 8, 5], in_dim=3, out_dim=2, act="gelu",
+                       pad_ratio=[0.125, 0.0625])
+    out["a12_pino_fno2d"] = model_case(f2, [torch.randn(2, 16, 12, 3)], None, dict(pad_ratio=[0.125, 0.0625]))
+    f2n = ref.PinoFNO2d(modes1=[4] * 2, modes2=[3] * 2, fc_dim=8, layers=[4, 6, 4], in_dim=3, out_dim=1, act="gelu")
+    out["a12_pino_fno2d_nopad"] = model_case(f2n, [torch.randn(2, 10, 14, 3)], None, {})
+
     only = os.environ.get("GOLDEN_ONLY")               # e.g. GOLDEN_ONLY=a10,a11: write just the new fixtures
     for k, v in out.items():
         if only and not any(k.startswith(p) for p in only.split(",")):

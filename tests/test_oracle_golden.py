@@ -142,3 +142,17 @@ def test_restated_pino_fullfield_and_policy(golden):
         for n, g in zip(names, gs):
             assert cf.rel_l2(g, c["grads"][n]) < 5e-5, (name, n)      # fp32 round-off of two op orders on 1e-9-sized gradients
     assert golden("a10_pinobserver_fullfield")["out"].shape == (2, 3, 8, 8, 9)      # planes first (pinobserver.py:360)
+
+
+def test_restated_pino_fno2d(golden):
+    """libs/models/pino_models/fourier2d.FNO2d (8f rank 4), with and without the two-sided zero padding."""
+    for name, m1, m2, layers in (("a12_pino_fno2d", [4] * 3, [3] * 3, [6, 8, 8, 5]), ("a12_pino_fno2d_nopad", [4] * 2, [3] * 2, [4, 6, 4])):
+        c = golden(name)
+        sd = {k: v.clone().requires_grad_(True) for k, v in c["state_dict"].items()}
+        out = rs.pino_fno2d_forward(sd, c["inputs"][0], m1, m2, layers, c.get("pad_ratio", (0.0, 0.0)))
+        assert out.shape == c["out"].shape
+        assert cf.rel_l2(out, c["out"]) < 5e-6, name
+        names = list(c["grads"].keys())
+        gs = torch.autograd.grad(out.square().mean(), [sd[n] for n in names])
+        for n, g in zip(names, gs):
+            assert cf.rel_l2(g, c["grads"][n]) < 5e-5, (name, n)
