@@ -262,6 +262,77 @@ __global__ void __launch_bounds__(128) k_t6(const float* __restrict__ A, const f
 }
 
 // -------------------------------------------------------------------------------------------------
+// T7: B = X^T as an MN-major operand (the transposed head backward needs it): X [C x NPX] pixel-contiguous, loaded by
+// TMA with the 128B / 32B-atom swizzle; A = W [128 x C] K-major no-swizzle.  D[m][p] = sum_c W[m][c] X[c][p], 3xTF32.
+// -------------------------------------------------------------------------------------------------
+template <int NPX, int C>
+__global__ void __launch_bounds__(128) k_t7(const __grid_constant__ CUtensorMap tmx, const float* __restrict__ W,
+                                            float* __restrict__ D) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int NB = NPX / 32;
+  uint8_t* sX = smem;                        // NB boxes of [C][32 px] = C*128 B each
+  uint8_t* sXlo = sX + NB * C * 128;
+  uint8_t* sWh = sXlo + NB * C * 128;
+  uint8_t* sWl = sWh + 128 * C * 4;
+  __shared__ uint64_t bar_tma, bar_mma;
+  __shared__ uint32_t tslot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 128 * C; i += 128) {
+    const int r = i / C, k = i % C;
+    const float w = W[i];
+    const float hi = tf32_rna(w);
+    *(float*)(sWh + kmajor_off(r, k, C)) = hi;
+    *(float*)(sWl + kmajor_off(r, k, C)) = tf32_rna(w - hi);
+  }
+  if (tid == 0) { mbar_init(&bar_tma, 1); mbar_init(&bar_mma, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(&tslot, NPX < 32 ? 32 : NPX);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tslot;
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bar_tma, NB * C * 128);
+    for (int j = 0; j < NB; j++) tma_load_3d(sX + j * C * 128, &tmx, &bar_tma, 32 * j, 0, 0);
+  }
+  mbar_wait(&bar_tma, 0);
+  for (int i = tid; i < NB * C * 32; i += 128) {
+    const float x = ((const float*)sX)[i];
+    ((float*)sXlo)[i] = tf32_lo(x);
+  }
+  fence_proxy_async();
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t idesc = idesc_tf32(128, NPX, 0, 1);
+    const uint32_t sbo_a = (C / 4) * 128;
+    int first = 1;
+    for (int pass = 0; pass < 3; pass++) {
+      const uint8_t* wa = pass == 1 ? sWl : sWh;
+      const uint8_t* xb = pass == 2 ? sXlo : sX;
+      for (int k = 0; k < C / 8; k++) {
+        const uint64_t da = smem_desc(smem_u32(wa) + k * 256, 128, sbo_a, LAYOUT_NONE);
+        // MN-major SW128_32B: 8 channel rows per K step (1024 B); groups of 32 px are C*128 B apart (LBO); SBO = 512 as for the A side
+        const uint64_t db = smem_desc(smem_u32(xb) + k * 1024, C * 128, 512, LAYOUT_SW128_32B);
+        mma_tf32_ss(tbase, da, db, idesc, first ? 0 : 1);
+        first = 0;
+      }
+    }
+    mma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  float v[16];
+  for (int c = 0; c < NPX; c += 16) {
+    tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + c, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; j++) D[(size_t)tid * NPX + c + j] = v[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, NPX < 32 ? 32 : NPX);
+}
+
+// -------------------------------------------------------------------------------------------------
 static float trunc_tf32(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; }
 static float rna_tf32(float x) {
   uint32_t u; memcpy(&u, &x, 4);
@@ -370,6 +441,32 @@ int main() {
     }
   }
 
+
+  // ---------------- T7: MN-major B operand from a TMA 128B_ATOM_32B tile ----------------
+  {
+    constexpr int NPX = 64, C = 32;
+    std::vector<float> X(C * NPX), W(128 * C), D(128 * NPX);
+    for (auto& v : X) v = frand();
+    for (auto& v : W) v = frand();
+    float *dX, *dW, *dD;
+    CK(cudaMalloc(&dX, X.size() * 4)); CK(cudaMalloc(&dW, W.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4));
+    CK(cudaMemcpy(dX, X.data(), X.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dD, 0, D.size() * 4));
+    CUtensorMap tm;
+    uint64_t dims[3] = {NPX, C, 1}, str[3] = {4, (uint64_t)NPX * 4, (uint64_t)NPX * C * 4};
+    uint32_t box[3] = {32, C, 1};
+    int rc = make_tmap_f32(&tm, dX, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) { printf("tensor map failed %d\n", rc); return 1; }
+    const int smem = 2 * (NPX / 32) * C * 128 + 2 * 128 * C * 4 + 1024;
+    CK(cudaFuncSetAttribute(k_t7<NPX, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_t7<NPX, C><<<1, 128, smem>>>(tm, dW, dD);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+    Err e = compare(D, 128, NPX, C, [&](int m, int k) { return W[m * C + k]; }, [&](int n, int k) { return X[k * NPX + n]; });
+    printf("T7 MN-major B (TMA SW128_32B), 3xTF32 : rel err vs exact %.3e  (expect ~4e-7; ~1 means the layout is not accepted)\n", e.exact);
+  }
   // ---------------- T6 / T7: MN-major no-swizzle operands ----------------
   {
     constexpr int N = 32, K = 128;
