@@ -91,8 +91,11 @@ def fdm_ns_vorticity(w: torch.Tensor, v: torch.Tensor, t_interval: float = 1.0) 
 
 def get_forcing(S: int, device=None, dtype=torch.float32) -> torch.Tensor:
     """libs/pino_utils/losses.py:288-291: -4 cos(4 y) on the periodic grid, shape (1, S, S, 1)."""
-    x2 = torch.arange(S, dtype=torch.float64) * (2.0 * math.pi / S)
-    return (-4.0 * torch.cos(4.0 * x2)).reshape(1, 1, S, 1).repeat(1, S, 1, 1).to(device=device, dtype=dtype)
+    # the grid is rounded to fp32 BEFORE the cosine, as the reference does (np.linspace in float64 -> torch.float):
+    # bit-identical forcing, including its ~1e-7 values where the exact cosine vanishes
+    x2 = (torch.arange(S, dtype=torch.float64) * (2.0 * math.pi / S)).to(torch.float32)
+    f = -4 * torch.cos(4 * x2)
+    return f.reshape(1, 1, S, 1).repeat(1, S, 1, 1).to(device=device, dtype=dtype)
 
 
 def _rel(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
