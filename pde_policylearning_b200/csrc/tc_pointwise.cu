@@ -547,7 +547,10 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
   if (!extras && !p.dact && p.act == B2NO_ACT_NONE && !p.preact) mode = 1;
   else if (!extras && !p.dact && p.act == B2NO_ACT_GELU) mode = 2;
   else if (!extras && p.dact == B2NO_ACT_GELU && p.act == B2NO_ACT_NONE && !p.preact) mode = 3;
-  if (mode == 3 && (((uintptr_t)p.dz & 15) == 0) && channels <= 256) p.Cz = b2no_round_up(channels, 8);
+  // dz through the TMA ring: enabled for the single-pass case (Co <= 32: every epilogue thread takes its 8 values and
+  // releases the stage at once), which is what the parity tests and the bench exercise; wider layers keep the per-thread
+  // loads until the multi-pass variant of the ring has its own GPU test
+  if (mode == 3 && (((uintptr_t)p.dz & 15) == 0) && channels <= kCW * kParts) p.Cz = b2no_round_up(channels, 8);
   // shared-memory budget -> number of stages
   int dev = 0, max_smem = 0;
   B2NO_CHECK_CUDA(cudaGetDevice(&dev));
