@@ -112,11 +112,16 @@ def test_geometry_matches_oracle():
 def test_convert_shares_parameters_with_reference_modules():
     import pde_policylearning_b200 as P
     from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("/root/reference is not mounted on this box")
     ref = ref_loader.load()
+    pino_kw = dict(modes1=[3] * 3, modes2=[3] * 3, modes3=[3] * 3, fc_dim=16, layers=[8] * 4, act="gelu", pad_ratio=0.0625)
     for build in (lambda: ref.FNO2d(12, 12, 32, in_channels=3, out_channels=1),
                   lambda: ref.RNO2d(12, 12, 34, 0, layer_num=1),
-                  lambda: ref.PINObserver2d(modes1=[3] * 3, modes2=[3] * 3, modes3=[3] * 3, fc_dim=16, layers=[8] * 4,
-                                            act="gelu", pad_ratio=0.0625)):
+                  lambda: ref.PINObserver2d(**pino_kw),
+                  # the other consumers of the PINO conv (pinobserver.py:276-463) are reached through convert_ as well
+                  lambda: ref.PINObserverFullField(plane_num=3, **pino_kw),
+                  lambda: ref.PolicyModel2D(**pino_kw)):
         r = build()
         before = {k: v.data_ptr() for k, v in r.named_parameters()}
         keys = list(r.state_dict().keys())
