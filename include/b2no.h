@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define B2NO_MAX_DIM 3
-#define B2NO_ABI_VERSION 2
+#define B2NO_ABI_VERSION 3
 
 enum { B2NO_NORM_BACKWARD = 0, B2NO_NORM_FORWARD = 1, B2NO_NORM_ORTHO = 2 };
 enum { B2NO_ACT_NONE = 0, B2NO_ACT_GELU = 1, B2NO_ACT_RELU = 2, B2NO_ACT_SIGMOID = 3, B2NO_ACT_SELU = 4,
@@ -73,8 +73,12 @@ typedef struct {
 /* Fused epilogue of the inverse transform:
  *   z = irfft(Yh) + bias[o] + sum_i pw_w[o,i] * pw_x[b,i,.] + sum_i pw2_w[o,i] * pw2_x[b,i,.] + add[b,o,.]
  *   y = act(z) * (mul ? mul[b,o,.] : 1) * (dact_z ? dact'(dact_z[b,o,.]) : 1)
- * (fno_block.py:131,142-150; rno.py:224-228,254-258; pinobserver.py:222-226).  pw_w is (Co, Ci) row-major,
- * or (Ci, Co) when pw_transposed (the dx pass of the 1x1 conv).  preact, when non-NULL, receives z. */
+ *       + (gate_z ? (1 - gate_z[b,o,.]) * gate_h[b,o,.] : 0)
+ * (fno_block.py:131,142-150; rno.py:224-228,254-259; pinobserver.py:222-226).  pw_w is (Co, Ci) row-major,
+ * or (Ci, Co) when pw_transposed (the dx pass of the 1x1 conv).  preact, when non-NULL, receives z.
+ * The gate term is the GRU-style state update of rno.py:259, h' = (1 - z) h + z2 hhat, with mul = z2: the candidate
+ * state hhat = act(.) never touches HBM.  mul_bstride / gate_bstride (floats between consecutive samples of mul /
+ * gate_z; 0 = dense, channels * pixels) let both gates be channel slices of ONE (batch, 2 C, grid) tensor. */
 typedef struct {
   const float* bias;
   const float* pw_w;  const float* pw_x;  int32_t pw_ci;  int32_t pw_transposed;
@@ -87,6 +91,10 @@ typedef struct {
    * pre-activation dact_z of the PREVIOUS layer, so a layer's dx pass emits gz of the layer below directly */
   const float* dact_z;
   int32_t dact;
+  const float* gate_z;
+  const float* gate_h;
+  int64_t mul_bstride;
+  int64_t gate_bstride;
 } b2no_epilogue;
 
 int b2no_version(void);
@@ -155,6 +163,16 @@ int b2no_rno_gate_fwd(const float* z, const float* z2, const float* hhat, const 
                       int64_t n, void* stream);
 int b2no_rno_gate_bwd(const float* g, const float* z, const float* z2, const float* hhat, const float* h,
                       float* gz, float* gz2, float* ghhat, float* gh, int64_t n, void* stream);
+/* Backward of the fused RNO cell update (rno.py:254-259), emitting the PRE-activation gradients of all gates at once:
+ *   h' = (1 - z) h + z2 selu(ah),  z = sigmoid(az), z2 = sigmoid(az2)   (zz2 = [z | z2] post-sigmoid, (batch, 2C, pixels))
+ *   g_zz2[:, :C] = -g h z (1 - z);  g_zz2[:, C:] = g selu(ah) z2 (1 - z2);  g_ah = g z2 selu'(ah);  g_h = g (1 - z)
+ * and of the reset gate r = sigmoid(ar) inside f6(r * h):
+ *   g_ar = g_rh h r (1 - r);  g_h += g_rh r
+ * n = batch, c = channels, p = pixels per channel; every tensor is dense (batch, channels, pixels). */
+int b2no_rno_cell_bwd(const float* g, const float* h, const float* zz2, const float* ah, float* g_zz2, float* g_ah,
+                      float* g_h, int batch, int c, int64_t p, void* stream);
+int b2no_rno_reset_bwd(const float* g_rh, const float* h, const float* ar, float* g_ar, float* g_h, int64_t n,
+                       void* stream);
 /* LpLoss.rel, p=2 (utilities3.py:323-334): per-sample sums -> sums[b] = (||x-y||^2, ||y||^2) */
 int b2no_rel_l2_sums(const float* x, const float* y, float* sums, int batch, int64_t n_per_sample, void* stream);
 /* dx = coef[b] * (x - y)  with coef[b] precomputed by the host from sums (and the upstream gradient) */
@@ -184,6 +202,12 @@ int64_t b2no_kernel_launches(void);
  * Replaces the per-parameter `p.grad += g` of run_pde_observers.py:192 (loss.backward()). */
 int b2no_gather_segments(float* flat, const void* src_ptrs, const int64_t* offsets, const int64_t* counts, int nseg,
                          void* stream);
+
+/* ---- measurement ---------------------------------------------------------------------------------- */
+/* Dense tcgen05.mma issue-rate probe for the roofline denominators ("measure a kind::tf32 GEMM on the box"):
+ * every SM issues n_mma back-to-back M=128, N=256 MMAs from resident shared-memory operands.  kind 0 = kind::tf32,
+ * 1 = kind::f16 (bf16 operands).  *flops receives the operation count of the launch; the caller times it with CUDA events. */
+int b2no_tc_peak_probe(int kind, int n_mma, double* flops, void* stream);
 
 #ifdef __cplusplus
 }

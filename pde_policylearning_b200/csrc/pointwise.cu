@@ -389,6 +389,96 @@ extern "C" int b2no_rno_gate_bwd(const float* g, const float* z, const float* z2
 }
 
 // ---------------------------------------------------------------------------------------------
+// Backward of the fused RNO cell update (the forward is the gate term of the inverse-transform epilogue): one pass
+// reads g, h, z, z2, ah and writes the pre-activation gradients of the three branches plus the direct dh term,
+// 128-bit vectorised (7 x 4 B per element: HBM-bound).  zz2 / g_zz2 are (batch, 2C, p): z in channels [0, C), z2 in [C, 2C).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_rno_cell_bwd(const float* __restrict__ g, const float* __restrict__ h, const float* __restrict__ zz2,
+               const float* __restrict__ ah, float* __restrict__ g_zz2, float* __restrict__ g_ah, float* __restrict__ g_h,
+               int B, long cp4) {
+  // cp4 = C * p / 4 float4 per sample; element (b, i) of the C-channel tensors sits at b * cp4 + i, of the 2C-channel ones
+  // at b * 2 cp4 + i (z) and b * 2 cp4 + cp4 + i (z2)
+  const long total = (long)B * cp4;
+  const long stride = (long)gridDim.x * blockDim.x;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  const float4* h4 = reinterpret_cast<const float4*>(h);
+  const float4* z4 = reinterpret_cast<const float4*>(zz2);
+  const float4* a4 = reinterpret_cast<const float4*>(ah);
+  float4* oz4 = reinterpret_cast<float4*>(g_zz2);
+  float4* oa4 = reinterpret_cast<float4*>(g_ah);
+  float4* oh4 = reinterpret_cast<float4*>(g_h);
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const long b = t / cp4, i = t - b * cp4;
+    const long iz = b * 2 * cp4 + i;
+    const float4 gv = __ldg(g4 + t), hv = __ldg(h4 + t), zv = __ldg(z4 + iz), z2v = __ldg(z4 + iz + cp4), av = __ldg(a4 + t);
+    float4 oz, oz2, oa, oh;
+#define B2NO_CELL(c)                                                          \
+    {                                                                         \
+      const float hh = b2no_act(av.c, B2NO_ACT_SELU);                         \
+      oz.c = -gv.c * hv.c * zv.c * (1.0f - zv.c);                             \
+      oz2.c = gv.c * hh * z2v.c * (1.0f - z2v.c);                             \
+      oa.c = gv.c * z2v.c * b2no_act_grad(av.c, B2NO_ACT_SELU);               \
+      oh.c = gv.c * (1.0f - zv.c);                                            \
+    }
+    B2NO_CELL(x) B2NO_CELL(y) B2NO_CELL(z) B2NO_CELL(w)
+#undef B2NO_CELL
+    oz4[iz] = oz;
+    oz4[iz + cp4] = oz2;
+    oa4[t] = oa;
+    oh4[t] = oh;
+  }
+}
+
+// reset gate inside f6(r * h):  g_ar = g_rh h r (1 - r),  g_h += g_rh r,  r = sigmoid(ar)
+__global__ void __launch_bounds__(256)
+k_rno_reset_bwd(const float* __restrict__ g_rh, const float* __restrict__ h, const float* __restrict__ ar,
+                float* __restrict__ g_ar, float* __restrict__ g_h, long n4) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  const float4* g4 = reinterpret_cast<const float4*>(g_rh);
+  const float4* h4 = reinterpret_cast<const float4*>(h);
+  const float4* a4 = reinterpret_cast<const float4*>(ar);
+  float4* o4 = reinterpret_cast<float4*>(g_ar);
+  float4* gh4 = reinterpret_cast<float4*>(g_h);
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += stride) {
+    const float4 gv = __ldg(g4 + t), hv = __ldg(h4 + t), av = __ldg(a4 + t);
+    float4 o, acc = gh4[t];
+#define B2NO_RST(c)                                                           \
+    {                                                                         \
+      const float r = b2no_act(av.c, B2NO_ACT_SIGMOID);                       \
+      o.c = gv.c * hv.c * r * (1.0f - r);                                     \
+      acc.c = fmaf(gv.c, r, acc.c);                                           \
+    }
+    B2NO_RST(x) B2NO_RST(y) B2NO_RST(z) B2NO_RST(w)
+#undef B2NO_RST
+    o4[t] = o;
+    gh4[t] = acc;
+  }
+}
+
+extern "C" int b2no_rno_cell_bwd(const float* g, const float* h, const float* zz2, const float* ah, float* g_zz2, float* g_ah,
+                                 float* g_h, int batch, int c, int64_t p, void* stream) {
+  if (!g || !h || !zz2 || !ah || !g_zz2 || !g_ah || !g_h || batch < 1 || c < 1 || p < 1) return B2NO_E_ARG;
+  const long cp = (long)c * p;
+  if (cp % 4) return B2NO_E_UNSUPPORTED;
+  if (((uintptr_t)g | (uintptr_t)h | (uintptr_t)zz2 | (uintptr_t)ah | (uintptr_t)g_zz2 | (uintptr_t)g_ah | (uintptr_t)g_h) & 15)
+    return B2NO_E_ARG;
+  k_rno_cell_bwd<<<(unsigned)grid_for((long)batch * (cp / 4), 256, 8), 256, 0, (cudaStream_t)stream>>>(g, h, zz2, ah, g_zz2, g_ah, g_h, batch, cp / 4);
+  B2NO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b2no_rno_reset_bwd(const float* g_rh, const float* h, const float* ar, float* g_ar, float* g_h, int64_t n,
+                                  void* stream) {
+  if (!g_rh || !h || !ar || !g_ar || !g_h || n < 1) return B2NO_E_ARG;
+  if (n % 4) return B2NO_E_UNSUPPORTED;
+  if (((uintptr_t)g_rh | (uintptr_t)h | (uintptr_t)ar | (uintptr_t)g_ar | (uintptr_t)g_h) & 15) return B2NO_E_ARG;
+  k_rno_reset_bwd<<<(unsigned)grid_for(n / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(g_rh, h, ar, g_ar, g_h, n / 4);
+  B2NO_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // relative L2: per-sample sums with warp-shuffle + block reduction, one atomicAdd pair per block
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -476,6 +476,8 @@ struct EpiDev {
   int act;
   const float* dz;
   int dact;
+  const float* gate_z; const float* gate_h;
+  long mul_bs, gate_bs;     // floats between consecutive samples of mul / gate_z (channel slices of a wider tensor)
 };
 
 template <int NPT, int OT>
@@ -595,8 +597,10 @@ k_c2r_fused(const float2* __restrict__ spec, float* __restrict__ y, const float*
             if (e.add) z += __ldg(e.add + idx);
             if (e.preact) e.preact[idx] = z;
             float v = b2no_act(z, e.act);
-            if (e.mul) v *= __ldg(e.mul + idx);
+            const size_t inner = (size_t)o * P + pix[j];
+            if (e.mul) v *= __ldg(e.mul + (size_t)b * e.mul_bs + inner);
             if (e.dz) v *= b2no_act_grad(__ldg(e.dz + idx), e.dact);
+            if (e.gate_z) v = fmaf(1.0f - __ldg(e.gate_z + (size_t)b * e.gate_bs + inner), __ldg(e.gate_h + idx), v);
             y[idx] = v;
           }
         }
@@ -646,7 +650,8 @@ extern "C" int b2no_dft_inverse(const b2no_plan* p, int which, const float* spec
     e.pw2_w = epi->pw2_w; e.pw2_x = epi->pw2_x; e.pw2_ci = (epi->pw2_w && epi->pw2_x) ? epi->pw2_ci : 0; e.pw2_t = epi->pw2_transposed;
     e.add = epi->add; e.mul = epi->mul; e.preact = epi->preact; e.act = epi->act;
     e.dz = epi->dact_z; e.dact = epi->dact_z ? epi->dact : 0;
-    if (e.pw_ci < 0 || e.pw2_ci < 0) return B2NO_E_ARG;
+    e.gate_z = (epi->gate_z && epi->gate_h) ? epi->gate_z : nullptr; e.gate_h = e.gate_z ? epi->gate_h : nullptr;
+    if (e.pw_ci < 0 || e.pw2_ci < 0 || epi->mul_bstride < 0 || epi->gate_bstride < 0) return B2NO_E_ARG;
   }
   // tensor-core tile kernel when the shape is eligible (tc_pointwise.cu); otherwise the CUDA-core kernels below
   if (epi && (spec == nullptr || (p && p->g.ndim == 2))) {
@@ -659,9 +664,14 @@ extern "C" int b2no_dft_inverse(const b2no_plan* p, int which, const float* spec
     const int rc = b2no_tc_pointwise(p, which, spec, y, work, batch, channels, px, epi, st);
     if (rc != 1) return rc;
   }
+  auto set_strides = [&](long P_) {
+    e.mul_bs = (epi && epi->mul_bstride) ? (long)epi->mul_bstride : (long)channels * P_;
+    e.gate_bs = (epi && epi->gate_bstride) ? (long)epi->gate_bstride : (long)channels * P_;
+  };
   if (!spec) {
     // pure pointwise op on a flattened grid
     if (pixels < 1) return B2NO_E_ARG;
+    set_strides(pixels);
     const int N = 128;
     const long RPI = (pixels + N - 1) / N;
     return run_c2r(nullptr, y, nullptr, e, batch, channels, RPI, N, pixels, 0, 128, st);
@@ -676,6 +686,7 @@ extern "C" int b2no_dft_inverse(const b2no_plan* p, int which, const float* spec
   long P = 1;
   for (int j = 0; j < d; j++) P *= n[j];
   if (pixels > 0 && pixels != P) return B2NO_E_ARG;
+  set_strides(P);
   if (d == 1) return run_c2r((const float2*)spec, y, tab, e, batch, channels, 1, n[0], P, Kl, npad, st);
   if (!work) return B2NO_E_ARG;
   float2* A = (float2*)work;

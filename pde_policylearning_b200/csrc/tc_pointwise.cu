@@ -51,6 +51,8 @@ struct PwTc {
   const float* w2; int w2_t;
   const float* ahi; const float* alo; const float* timg;
   const float* bias; const float* add; const float* mul; const float* dz;
+  const float* gate_z; const float* gate_h;
+  long mul_bs, gate_bs;   // floats between consecutive samples of mul / gate_z
   float* preact; float* y;
   int act, dact;
   int debug;          // bit0 no stores, bit1 no MMAs
@@ -347,14 +349,17 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
         float v[kCW];
         tmem_ld8(tbase + lane_base + (uint32_t)(a * p.Np + c0), v);
         if (MODE == 0) {
-          float av[kCW], mv[kCW], dv[kCW];
+          float av[kCW], mv[kCW], dv[kCW], gzv[kCW], ghv[kCW];
 #pragma unroll
           for (int j = 0; j < kCW; j++) {
             const bool ok = c0 + j < p.Co;
             const size_t idx = base + (size_t)(c0 + j) * p.P;
+            const size_t inner = (size_t)(c0 + j) * p.P + px;
             av[j] = (p.add && ok) ? __ldg(p.add + idx) : 0.f;
-            mv[j] = (p.mul && ok) ? __ldg(p.mul + idx) : 1.f;
+            mv[j] = (p.mul && ok) ? __ldg(p.mul + (size_t)b * p.mul_bs + inner) : 1.f;
             dv[j] = (p.dz && ok) ? __ldg(p.dz + idx) : 0.f;
+            gzv[j] = (p.gate_z && ok) ? __ldg(p.gate_z + (size_t)b * p.gate_bs + inner) : 1.f;
+            ghv[j] = (p.gate_z && ok) ? __ldg(p.gate_h + idx) : 0.f;
           }
           tmem_ld_wait();
 #pragma unroll
@@ -363,7 +368,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
               const size_t idx = base + (size_t)(c0 + j) * p.P;
               const float z = v[j] + sbias[c0 + j] + av[j];
               if (p.preact) p.preact[idx] = z;
-              const float r = epi_value<0>(z, mv[j], dv[j], p.act, p.dact);
+              const float r = fmaf(1.0f - gzv[j], ghv[j], epi_value<0>(z, mv[j], dv[j], p.act, p.dact));
               if (!nostore) p.y[idx] = r;
             }
           }
@@ -530,6 +535,9 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
   p.w1 = e->pw_w; p.w1_t = e->pw_transposed; p.w2 = has2 ? e->pw2_w : nullptr; p.w2_t = e->pw2_transposed;
   p.bias = e->bias; p.add = e->add; p.mul = e->mul; p.dz = e->dact_z; p.preact = e->preact; p.y = y;
   p.act = e->act; p.dact = e->dact_z ? e->dact : 0;
+  p.gate_z = (e->gate_z && e->gate_h) ? e->gate_z : nullptr; p.gate_h = p.gate_z ? e->gate_h : nullptr;
+  p.mul_bs = e->mul_bstride ? (long)e->mul_bstride : (long)channels * pixels;
+  p.gate_bs = e->gate_bstride ? (long)e->gate_bstride : (long)channels * pixels;
   if (spec) {
     if (!plan || plan->g.ndim != 2 || !work) return 1;
     const b2no_tc_tables& tt = plan->tc[which];
@@ -542,7 +550,7 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
     p.alo = work + afl;
   }
   if (pw_tmem_cols(p) > 512) return 1;
-  const bool extras = p.add || p.mul;
+  const bool extras = p.add || p.mul || p.gate_z;
   int mode = 0;
   if (!extras && !p.dact && p.act == B2NO_ACT_NONE && !p.preact) mode = 1;
   else if (!extras && !p.dact && p.act == B2NO_ACT_GELU) mode = 2;

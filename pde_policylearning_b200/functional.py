@@ -382,3 +382,223 @@ class RnoGateFn(torch.autograd.Function):
 
 def rno_gate(z, z2, hhat, h):
     return RnoGateFn.apply(z, z2, hhat, h)
+
+
+# =============================================================================================
+# RNO layer: the GRU-style recurrent cell of rno.py:254-290 as ONE autograd node over all time steps
+# =============================================================================================
+_RNO_XCHUNK = 8192      # planes-batches per x-side launch (bounds the A' workspace and gridDim.y)
+
+
+class RnoLayerFn(torch.autograd.Function):
+    """h_t = cell(x_t, h_{t-1}) for t = 0..T'-1 (RNO_layer.forward, rno.py:275-290; RNO_cell.forward, rno.py:254-260).
+
+    The reference evaluates eight FourierLayer2d per step, each with its own rfft2 / irfft2.  Every f_k is LINEAR, so the
+    cell is regrouped (same sums):
+
+      x side, no recurrence -> hoisted over ALL T' frames and batched:   Xh = F(x);  Gx_g = F^-1(Xh W_g) + P_g x + bias_g
+                                                                         for the gate groups g = [z | z2], r, hhat
+      h side, per step:   Hh = F(h)
+                          [z | z2] = sigmoid(F^-1(Hh [W2 | W8]) + [Wc2; Wc8] h + Gx_zz2[t])          one inverse, 2C channels
+                          r h      = sigmoid(F^-1(Hh W4) + Wc4 h + Gx_r[t]) * h                       `mul` epilogue
+                          h'       = (1 - z) h + z2 selu(F^-1(F(r h) W6) + Wc6 (r h) + Gx_h[t])      gate epilogue
+
+    i.e. 2 forward + 3 inverse transforms per recurrent step instead of 8 + 8, all sigmoid / SELU / gate arithmetic inside
+    the inverse-transform epilogues.  The backward walks the steps in reverse (BPTT) with the adjoint kernels, accumulating
+    the weight gradients of all steps in place, and does the x side once, batched.
+
+    x_tm: (T', B, C, H, W) time-major; h0: (B, C, H, W); params: for k = 1..8 (fourier_weight.0, fourier_weight.1,
+    norm_conv1d.weight, norm_conv1d.bias), then b1..b4 (rno.py:249-252)."""
+
+    @staticmethod
+    def forward(ctx, x_tm, h0, geom: SpecGeom, return_sequences: bool, *params):
+        ops._require_cuda(x_tm, h0)
+        x_tm, h0 = _contig(x_tm.float()), _contig(h0.float())
+        Tn, B, Cc, H, W = x_tm.shape
+        plan = get_plan(geom, x_tm.device)
+        pk = _rno_pack(params, Cc)
+        xf = x_tm.reshape(Tn * B, Cc, H, W)
+        # ---- x side, batched over frames ----
+        Gzz2 = torch.empty((Tn * B, 2 * Cc, H, W), dtype=torch.float32, device=xf.device)
+        Gr = torch.empty((Tn * B, Cc, H, W), dtype=torch.float32, device=xf.device)
+        Gh = torch.empty_like(Gr)
+        Xh = torch.empty((Tn * B, Cc) + plan.kept, dtype=torch.complex64, device=xf.device)
+        for s in range(0, Tn * B, _RNO_XCHUNK):
+            e = min(Tn * B, s + _RNO_XCHUNK)
+            xs = xf[s:e]
+            xh = ops.dft_forward(plan, 0, xs, out=Xh[s:e])
+            for Wc, Pm, bias, co, G in ((pk["Wx_zz2"], pk["Px_zz2"], pk["bias_zz2"], 2 * Cc, Gzz2),
+                                        (pk["Wx_r"], pk["Px_r"], pk["bias_r"], Cc, Gr),
+                                        (pk["Wx_h"], pk["Px_h"], pk["bias_h"], Cc, Gh)):
+                S = ops.mix(plan, 0, xh, Wc, Cc, co)
+                ops.dft_inverse(plan, 0, S, ops.make_epilogue(bias=bias, pw_w=Pm, pw_x=xs), out=G[s:e])
+        Gzz2, Gr, Gh = (G.reshape(Tn, B, -1, H, W) for G in (Gzz2, Gr, Gh))
+        # ---- recurrence ----
+        need_grad = any(ctx.needs_input_grad)
+        hs = []
+        saved = []
+        h = h0
+        for t in range(Tn):
+            Hh = ops.dft_forward(plan, 0, h)
+            S = ops.mix(plan, 0, Hh, pk["Wh_zz2"], Cc, 2 * Cc)
+            zz2 = ops.dft_inverse(plan, 0, S, ops.make_epilogue(pw_w=pk["Ph_zz2"], pw_x=h, add=Gzz2[t], act="sigmoid"))
+            S = ops.mix(plan, 0, Hh, pk["Wh_r"], Cc, Cc)
+            ar = torch.empty_like(h) if need_grad else None
+            rh = ops.dft_inverse(plan, 0, S, ops.make_epilogue(pw_w=pk["Ph_r"], pw_x=h, add=Gr[t], act="sigmoid", mul=h,
+                                                                preact=ar))
+            RHh = ops.dft_forward(plan, 0, rh)
+            S = ops.mix(plan, 0, RHh, pk["W6"], Cc, Cc)
+            ah = torch.empty_like(h) if need_grad else None
+            hn = ops.dft_inverse(plan, 0, S, ops.make_epilogue(pw_w=pk["P6"], pw_x=rh, add=Gh[t], act="selu", preact=ah,
+                                                                mul=zz2[:, Cc:], gate_z=zz2[:, :Cc], gate_h=h))
+            if return_sequences:
+                hs.append(hn)
+            if need_grad:
+                saved += [h, Hh, zz2, ar, rh, RHh, ah]
+            h = hn
+        ctx.geom, ctx.dims, ctx.return_sequences = geom, (Tn, B, Cc, H, W), return_sequences
+        ctx.param_shapes = [tuple(p.shape) for p in params]
+        if need_grad:
+            ctx.save_for_backward(xf, Xh, *[p.detach() for p in params], *saved)
+        return torch.stack(hs, dim=0) if return_sequences else h
+
+    @staticmethod
+    def backward(ctx, gout):
+        Tn, B, Cc, H, W = ctx.dims
+        geom = ctx.geom
+        sv = ctx.saved_tensors
+        xf, Xh = sv[0], sv[1]
+        params = sv[2:38]
+        steps = sv[38:]
+        plan = get_plan(geom, xf.device)
+        pk = _rno_pack(params, Cc)
+        dev = xf.device
+        gout = _contig(gout.float())
+        gGzz2 = torch.empty((Tn, B, 2 * Cc, H, W), dtype=torch.float32, device=dev)
+        gGr = torch.empty((Tn, B, Cc, H, W), dtype=torch.float32, device=dev)
+        gGh = torch.empty_like(gGr)
+        overlap = _geom_has_overlap(geom)
+        zl = torch.zeros_like if overlap else torch.empty_like
+        dWh_zz2 = [zl(w) for w in pk["Wh_zz2"]]
+        dWh_r = [zl(w) for w in pk["Wh_r"]]
+        dW6 = [zl(w) for w in pk["W6"]]
+        dPh_zz2 = dPh_r = dP6 = None
+
+        def acc_(a, d):
+            return d if a is None else a.add_(d)
+
+        g = gout[Tn - 1] if ctx.return_sequences else gout
+        first = True
+        for t in range(Tn - 1, -1, -1):
+            h, Hh, zz2, ar, rh, RHh, ah = steps[7 * t: 7 * t + 7]
+            if ctx.return_sequences and t < Tn - 1:
+                g = g + gout[t]
+            g_hdir = ops.rno_cell_bwd(_contig(g), h, zz2, ah, gGzz2[t], gGh[t])
+            g_ah = gGh[t]
+            # candidate-state branch: a_h = F^-1(F(rh) W6) + Wc6 rh + Gx_h
+            gY = ops.dft_forward(plan, 1, g_ah)
+            ops.mix_dw(plan, RHh, gY, pk["W6"], False, out=dW6, accumulate=not first)
+            gRH = ops.mix(plan, 1, gY, pk["W6"], Cc, Cc)
+            g_rh = ops.dft_inverse(plan, 1, gRH, ops.make_epilogue(pw_w=pk["P6"], pw_x=g_ah, pw_transposed=True))
+            dP6 = acc_(dP6, ops.pw_wgrad(g_ah, rh, need_bias=False)[0])
+            ops.rno_reset_bwd(g_rh, h, ar, gGr[t], g_hdir)
+            g_azz2, g_ar = gGzz2[t], gGr[t]
+            # gates: [a_z | a_z2] and a_r, all functions of h
+            gYz = ops.dft_forward(plan, 1, g_azz2)
+            gYr = ops.dft_forward(plan, 1, g_ar)
+            ops.mix_dw(plan, Hh, gYz, pk["Wh_zz2"], False, out=dWh_zz2, accumulate=not first)
+            ops.mix_dw(plan, Hh, gYr, pk["Wh_r"], False, out=dWh_r, accumulate=not first)
+            gH = ops.mix(plan, 1, gYz, pk["Wh_zz2"], Cc, 2 * Cc)
+            ops.mix(plan, 1, gYr, pk["Wh_r"], Cc, Cc, out=gH, accumulate=True)
+            t1 = ops.pointwise(B, Cc, (H, W), dev, ops.make_epilogue(pw_w=pk["Ph_zz2"], pw_x=g_azz2, pw_transposed=True,
+                                                                     add=g_hdir))
+            g = ops.dft_inverse(plan, 1, gH, ops.make_epilogue(pw_w=pk["Ph_r"], pw_x=g_ar, pw_transposed=True, add=t1))
+            dPh_zz2 = acc_(dPh_zz2, ops.pw_wgrad(g_azz2, h, need_bias=False)[0])
+            dPh_r = acc_(dPh_r, ops.pw_wgrad(g_ar, h, need_bias=False)[0])
+            first = False
+        g_h0 = g if ctx.needs_input_grad[1] else None
+        # ---- x side, batched ----
+        need_x = ctx.needs_input_grad[0]
+        gx = torch.empty_like(xf) if need_x else None
+        dWx = {k: [zl(w) for w in pk[k]] for k in ("Wx_zz2", "Wx_r", "Wx_h")}
+        dPx, dbx = {}, {}
+        groups = (("Wx_zz2", "Px_zz2", gGzz2.reshape(Tn * B, 2 * Cc, H, W), 2 * Cc),
+                  ("Wx_r", "Px_r", gGr.reshape(Tn * B, Cc, H, W), Cc),
+                  ("Wx_h", "Px_h", gGh.reshape(Tn * B, Cc, H, W), Cc))
+        firstc = True
+        for s in range(0, Tn * B, _RNO_XCHUNK):
+            e = min(Tn * B, s + _RNO_XCHUNK)
+            xs, xh = xf[s:e], Xh[s:e]
+            gX = None
+            for wk, pkey, G, co in groups:
+                gs = G[s:e]
+                gY = ops.dft_forward(plan, 1, gs)
+                ops.mix_dw(plan, xh, gY, pk[wk], False, out=dWx[wk], accumulate=not firstc)
+                dw, db = ops.pw_wgrad(gs, xs, need_bias=True)
+                dPx[pkey] = acc_(dPx.get(pkey), dw)
+                dbx[pkey] = acc_(dbx.get(pkey), db)
+                if need_x:
+                    if gX is None:
+                        gX = ops.mix(plan, 1, gY, pk[wk], Cc, co)
+                    else:
+                        ops.mix(plan, 1, gY, pk[wk], Cc, co, out=gX, accumulate=True)
+            if need_x:
+                n = e - s
+                t1 = ops.pointwise(n, Cc, (H, W), dev, ops.make_epilogue(pw_w=pk["Px_zz2"], pw_x=groups[0][2][s:e],
+                                                                         pw_transposed=True))
+                t2 = ops.pointwise(n, Cc, (H, W), dev, ops.make_epilogue(pw_w=pk["Px_h"], pw_x=groups[2][2][s:e],
+                                                                         pw_transposed=True, add=t1))
+                ops.dft_inverse(plan, 1, gX, ops.make_epilogue(pw_w=pk["Px_r"], pw_x=groups[1][2][s:e], pw_transposed=True,
+                                                               add=t2), out=gx[s:e])
+            firstc = False
+        # ---- unpack into the reference's parameters ----
+        C = Cc
+        sp = {1: (dWx["Wx_zz2"], 0), 7: (dWx["Wx_zz2"], 1), 3: (dWx["Wx_r"], None), 5: (dWx["Wx_h"], None),
+              2: (dWh_zz2, 0), 8: (dWh_zz2, 1), 4: (dWh_r, None), 6: (dW6, None)}
+        pw = {1: (dPx["Px_zz2"], 0), 7: (dPx["Px_zz2"], 1), 3: (dPx["Px_r"], None), 5: (dPx["Px_h"], None),
+              2: (dPh_zz2, 0), 8: (dPh_zz2, 1), 4: (dPh_r, None), 6: (dP6, None)}
+        db_zz2, db_r, db_h = dbx["Px_zz2"], dbx["Px_r"], dbx["Px_h"]
+        cbg = {1: db_zz2[:C], 2: db_zz2[:C], 7: db_zz2[C:], 8: db_zz2[C:], 3: db_r, 4: db_r, 5: db_h, 6: db_h}
+        grads = []
+        for k in range(1, 9):
+            gl, half = sp[k]
+            for j in (0, 1):
+                w = gl[j] if half is None else gl[j][:, half * C:(half + 1) * C]
+                grads.append(w.reshape(ctx.param_shapes[4 * (k - 1) + j]))
+            m, half = pw[k]
+            m = m if half is None else m[half * C:(half + 1) * C]
+            grads.append(m.reshape(ctx.param_shapes[4 * (k - 1) + 2]))
+            grads.append(cbg[k].reshape(ctx.param_shapes[4 * (k - 1) + 3]))
+        for v in (db_zz2[:C], db_r, db_h, db_zz2[C:]):            # b1, b2, b3, b4 (rno.py:255-258)
+            grads.append(v.sum().reshape(()))
+        gx_out = gx.reshape(Tn, B, Cc, H, W) if need_x else None
+        return (gx_out, g_h0, None, None) + tuple(grads)
+
+
+def _rno_pack(params, C):
+    """Gate-grouped operands of the regrouped cell (concatenated along the OUTPUT channel): the reference's parameters are
+    only read, the packs are rebuilt from them at every call (a few MB)."""
+    P_ = [p.detach() for p in params]
+    fw = lambda k, j: P_[4 * (k - 1) + j]
+    cw = lambda k: P_[4 * (k - 1) + 2].reshape(C, C).float()
+    cb = lambda k: P_[4 * (k - 1) + 3].float()
+    b1, b2, b3, b4 = (P_[32 + i].float() for i in range(4))
+    cat = torch.cat
+    return {
+        "Wx_zz2": [cat((fw(1, j), fw(7, j)), dim=1).contiguous() for j in (0, 1)],
+        "Wx_r": [_contig(fw(3, j)) for j in (0, 1)], "Wx_h": [_contig(fw(5, j)) for j in (0, 1)],
+        "Wh_zz2": [cat((fw(2, j), fw(8, j)), dim=1).contiguous() for j in (0, 1)],
+        "Wh_r": [_contig(fw(4, j)) for j in (0, 1)], "W6": [_contig(fw(6, j)) for j in (0, 1)],
+        "Px_zz2": cat((cw(1), cw(7)), dim=0).contiguous(), "Px_r": _contig(cw(3)), "Px_h": _contig(cw(5)),
+        "Ph_zz2": cat((cw(2), cw(8)), dim=0).contiguous(), "Ph_r": _contig(cw(4)), "P6": _contig(cw(6)),
+        "bias_zz2": cat((cb(1) + cb(2) + b1, cb(7) + cb(8) + b4)).contiguous(),
+        "bias_r": (cb(3) + cb(4) + b2).contiguous(), "bias_h": (cb(5) + cb(6) + b3).contiguous(),
+    }
+
+
+def rno_layer_supported(x, C, H, W) -> bool:
+    return x.is_cuda and H == W and (C * H * W) % 4 == 0
+
+
+def rno_layer(x_tm, h0, geom: SpecGeom, return_sequences, params):
+    return RnoLayerFn.apply(x_tm, h0, geom, bool(return_sequences), *params)

@@ -543,7 +543,24 @@ class RNO_cell(nn.Module):
         for k in range(1, 5):
             setattr(self, f"b{k}", nn.Parameter(torch.normal(torch.tensor(0.), torch.tensor(1.))))
 
+    def _params(self):
+        ps = []
+        for k in range(1, 9):
+            f = getattr(self, f"f{k}")
+            ps += [f.spec_conv.fourier_weight[0], f.spec_conv.fourier_weight[1], f.norm_conv1d.weight, f.norm_conv1d.bias]
+        return ps + [self.b1, self.b2, self.b3, self.b4]
+
+    def forward_sequence(self, x_tm, h, return_sequences=False):
+        """x_tm: (T', B, C, H, W) time-major.  All T' recurrent steps as ONE autograd node (functional.RnoLayerFn): the
+        x-dependent halves f1, f3, f5, f7 hoisted over the frames, gates batched, activations in the epilogues."""
+        Tn, B, C, H, W = x_tm.shape
+        geom = self.f1.spec_conv.geom((H, W))
+        return Fn.rno_layer(x_tm, h, geom, return_sequences, self._params())
+
     def forward(self, x, h):
+        if Fn.rno_layer_supported(x, x.shape[1], x.shape[2], x.shape[3]) and x.shape == h.shape:
+            return self.forward_sequence(x.unsqueeze(0), h)
+        # shapes without the regrouped path (non-square grids, rno.py:66-67 crop / zero-pad): the reference's composition
         z = torch.sigmoid(self.f1(x) + self.f2(h, extra_bias=self.b1))
         z2 = torch.sigmoid(self.f7(x) + self.f8(h, extra_bias=self.b4))
         r = torch.sigmoid(self.f3(x) + self.f4(h, extra_bias=self.b2))
@@ -561,16 +578,27 @@ class RNO_layer(nn.Module):
         self.cell = RNO_cell(in_dim, out_dim, modes1, modes2, width)
         self.bias_h = nn.Parameter(torch.normal(torch.tensor(0.), torch.tensor(1.)))
 
-    def forward(self, x, h=None):
-        batch_size, timesteps, dim, s1, s2 = x.shape
+    def forward(self, x, h=None, time_major=False):
+        """x: (B, T', C, H, W) as in the reference, or (T', B, C, H, W) with time_major (what RNO2d passes: the frames of
+        one step are then contiguous, which is what the per-step kernels want)."""
+        if time_major:
+            timesteps, batch_size, dim, s1, s2 = x.shape
+        else:
+            batch_size, timesteps, dim, s1, s2 = x.shape
         if h is None:
             h = torch.zeros((batch_size, self.width, s1, s2), device=x.device) + self.bias_h
+        if Fn.rno_layer_supported(x, dim, s1, s2) and dim == self.width:
+            x_tm = x if time_major else x.transpose(0, 1)
+            out = self.cell.forward_sequence(x_tm, h, self.return_sequences)
+            if self.return_sequences and not time_major:
+                out = out.transpose(0, 1)
+            return out
         outputs = []
         for i in range(timesteps):
-            h = self.cell(x[:, i], h)
+            h = self.cell(x[i] if time_major else x[:, i], h)
             if self.return_sequences:
                 outputs.append(h)
-        return torch.stack(outputs, dim=1) if self.return_sequences else h
+        return torch.stack(outputs, dim=0 if time_major else 1) if self.return_sequences else h
 
 
 class SpectralConvWithFC(nn.Module):
@@ -659,10 +687,12 @@ class RNO2d(nn.Module):
         if init_hidden_states is None:
             init_hidden_states = [None] * self.layer_num
         B, T, s1, s2, dim = x.shape
-        # Linear(1 -> width) on channels-last == 1x1 conv on (B*T, 1, s1, s2)
-        xc = Fn.pointwise_conv(x.reshape(B * T, dim, s1, s2) if dim == 1 else x.permute(0, 1, 4, 2, 3).reshape(B * T, dim, s1, s2),
-                               self.input_projection_layer.weight, self.input_projection_layer.bias, None)
-        x = xc.reshape(B, T, self.width, s1, s2)
+        # Linear(in_dim -> width) on channels-last == 1x1 conv on (T*B, in_dim, s1, s2); the frames go time-major so that
+        # every recurrent step reads one contiguous (B, C, s1, s2) block
+        xt = x.transpose(0, 1)
+        xin = xt.reshape(T * B, dim, s1, s2) if dim == 1 else xt.permute(0, 1, 4, 2, 3).reshape(T * B, dim, s1, s2)
+        xc = Fn.pointwise_conv(xin, self.input_projection_layer.weight, self.input_projection_layer.bias, None)
+        x = xc.reshape(T, B, self.width, s1, s2)
         if self.pad_amount:
             if self.pad_dim == "1":
                 x = F.pad(x.permute(0, 1, 2, 4, 3), [0, self.pad_amount[0]]).permute(0, 1, 2, 4, 3)
@@ -673,10 +703,10 @@ class RNO2d(nn.Module):
                 x = F.pad(x, [0, self.pad_amount[1]])
         finals = []
         for i in range(self.layer_num):
-            pred_x = self.layers[i](x, init_hidden_states[i])
+            pred_x = self.layers[i](x, init_hidden_states[i], time_major=True)
             if i < self.layer_num - 1:
                 x = x + pred_x
-                finals.append(x[:, -1])
+                finals.append(x[-1])
             else:
                 x = pred_x
                 finals.append(x)

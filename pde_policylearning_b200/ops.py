@@ -169,7 +169,7 @@ def weights_struct(corners: Sequence[torch.Tensor], ndim: int) -> Weights:
 # ---------------------------------------------------------------------------------------------
 # raw ops
 # ---------------------------------------------------------------------------------------------
-def dft_forward(plan: Plan, which: int, x: torch.Tensor) -> torch.Tensor:
+def dft_forward(plan: Plan, which: int, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x (B, C, *grid) fp32 contiguous -> spectrum (B, C, *kept) complex64."""
     _require_cuda(x)
     assert x.dtype == torch.float32 and x.is_contiguous()
@@ -177,7 +177,11 @@ def dft_forward(plan: Plan, which: int, x: torch.Tensor) -> torch.Tensor:
     grid = plan.geom.nin if which == 0 else plan.geom.nout
     if tuple(x.shape[2:]) != tuple(grid):
         raise ValueError(f"expected grid {tuple(grid)}, got {tuple(x.shape[2:])}")
-    spec = torch.empty((B, Cc) + plan.kept, dtype=torch.complex64, device=x.device)
+    if out is None:
+        spec = torch.empty((B, Cc) + plan.kept, dtype=torch.complex64, device=x.device)
+    else:
+        spec = out
+        assert spec.dtype == torch.complex64 and spec.is_contiguous() and tuple(spec.shape) == (B, Cc) + plan.kept
     work = plan.workspace(B, Cc)
     check(_lib.lib().b2no_dft_forward(plan.handle, which, _ptr(x), _ptr(spec), _ptr(work), B * Cc, _stream()),
           "dft_forward")
@@ -185,16 +189,28 @@ def dft_forward(plan: Plan, which: int, x: torch.Tensor) -> torch.Tensor:
 
 
 def make_epilogue(bias=None, pw_w=None, pw_x=None, pw_transposed=False, pw2_w=None, pw2_x=None,
-                  pw2_transposed=False, add=None, mul=None, preact=None, act=None, dact_z=None, dact=None) -> Epilogue:
+                  pw2_transposed=False, add=None, mul=None, preact=None, act=None, dact_z=None, dact=None,
+                  gate_z=None, gate_h=None) -> Epilogue:
+    """mul / gate_z may be channel slices ``t[:, a:b]`` of a wider contiguous (batch, channels, *grid) tensor: their batch
+    stride is passed to the kernel (b2no_epilogue.mul_bstride / gate_bstride)."""
     e = Epilogue()
     keep = []
     for name, t in (("bias", bias), ("pw_w", pw_w), ("pw_x", pw_x), ("pw2_w", pw2_w), ("pw2_x", pw2_x),
-                    ("add", add), ("mul", mul), ("preact", preact), ("dact_z", dact_z)):
+                    ("add", add), ("mul", mul), ("preact", preact), ("dact_z", dact_z), ("gate_z", gate_z),
+                    ("gate_h", gate_h)):
         if t is not None:
             _require_cuda(t)
-            assert t.dtype == torch.float32 and t.is_contiguous(), name
+            assert t.dtype == torch.float32, name
+            if name in ("mul", "gate_z") and not t.is_contiguous():
+                # a channel slice: dense inside a sample, batch stride of the parent tensor
+                assert t.dim() >= 2 and t[0].is_contiguous(), name
+                setattr(e, name + "_bstride" if name == "mul" else "gate_bstride", t.stride(0))
+            else:
+                assert t.is_contiguous(), name
             setattr(e, name, t.data_ptr())
             keep.append(t)
+    if (gate_z is None) != (gate_h is None):
+        raise ValueError("gate_z and gate_h go together")
     if pw_w is not None:
         e.pw_ci = pw_x.shape[1]
         e.pw_transposed = 1 if pw_transposed else 0
@@ -248,14 +264,21 @@ def mix(plan: Plan, mode: int, spec: torch.Tensor, corners: Sequence[torch.Tenso
     return out
 
 
-def mix_dw(plan: Plan, xh: torch.Tensor, gyh: torch.Tensor, like: Sequence[torch.Tensor], needs_zero: bool):
-    """Returns the list of corner gradients shaped/typed like `like`."""
+def mix_dw(plan: Plan, xh: torch.Tensor, gyh: torch.Tensor, like: Sequence[torch.Tensor], needs_zero: bool,
+           out: Optional[Sequence[torch.Tensor]] = None, accumulate: bool = False):
+    """Returns the list of corner gradients shaped/typed like `like`; with `out` (contiguous tensors of that shape) the
+    gradients are written -- or, with accumulate, added -- in place (BPTT over the recurrent steps of the RNO)."""
     B, ci = xh.shape[:2]
     co = gyh.shape[1]
-    alloc = torch.zeros_like if needs_zero else torch.empty_like
-    grads = [alloc(t, memory_format=torch.contiguous_format) for t in like]
+    if out is None:
+        alloc = torch.zeros_like if needs_zero else torch.empty_like
+        grads = [alloc(t, memory_format=torch.contiguous_format) for t in like]
+        accumulate = False
+    else:
+        grads = list(out)
     w = weights_struct(grads, plan.geom.ndim)
-    check(_lib.lib().b2no_mix_dw(plan.handle, _ptr(xh), _ptr(gyh), C.byref(w), B, ci, co, 0, _stream()), "mix_dw")
+    check(_lib.lib().b2no_mix_dw(plan.handle, _ptr(xh), _ptr(gyh), C.byref(w), B, ci, co, 1 if accumulate else 0,
+                                 _stream()), "mix_dw")
     return grads
 
 
@@ -330,6 +353,27 @@ def rno_gate_bwd(g, z, z2, hh, h):
     check(_lib.lib().b2no_rno_gate_bwd(_ptr(g), _ptr(z), _ptr(z2), _ptr(hh), _ptr(h), *[_ptr(o) for o in outs],
                                        h.numel(), _stream()), "gate_bwd")
     return outs
+
+
+def rno_cell_bwd(g, h, zz2, ah, g_zz2, g_ah):
+    """Pre-activation gradients of the fused RNO cell update (see include/b2no.h); g_zz2 / g_ah are written in place,
+    returns the direct dh term g (1 - z)."""
+    B, Cc = h.shape[:2]
+    P = math.prod(h.shape[2:])
+    g_h = torch.empty_like(h)
+    for t in (g, h, zz2, ah, g_zz2, g_ah):
+        assert t.is_contiguous() and t.dtype == torch.float32
+    check(_lib.lib().b2no_rno_cell_bwd(_ptr(g), _ptr(h), _ptr(zz2), _ptr(ah), _ptr(g_zz2), _ptr(g_ah), _ptr(g_h), B, Cc, P,
+                                       _stream()), "rno_cell_bwd")
+    return g_h
+
+
+def rno_reset_bwd(g_rh, h, ar, g_ar, g_h):
+    """g_ar = g_rh h r (1 - r) (written in place), g_h += g_rh r, with r = sigmoid(ar)."""
+    for t in (g_rh, h, ar, g_ar, g_h):
+        assert t.is_contiguous() and t.dtype == torch.float32
+    check(_lib.lib().b2no_rno_reset_bwd(_ptr(g_rh), _ptr(h), _ptr(ar), _ptr(g_ar), _ptr(g_h), h.numel(), _stream()),
+          "rno_reset_bwd")
 
 
 def rel_l2_sums(x, y):
