@@ -158,7 +158,7 @@ def cpu_reference_run(steps, warmup, sample_batch):
 # ---------------------------------------------------------------------------------------------
 # per-kernel probes (CUDA events on the launching stream) for the roofline object
 # ---------------------------------------------------------------------------------------------
-def _time_op(fn, iters=10, warm=3):
+def _time_op(fn, iters=30, warm=5):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -172,10 +172,35 @@ def _time_op(fn, iters=10, warm=3):
     return sum(ts) / len(ts) * 1e-3  # seconds, mean
 
 
+def measured_tc_peaks(dev):
+    """Dense tcgen05.mma issue rate measured on this GPU (csrc/tc_peak.cu: every SM issues back-to-back M=128, N=256 MMAs
+    from resident shared-memory operands, cta_group::1), CUDA events around the launch, best of 5.  SURVEY.md 8d asked
+    for a measured kind::tf32 figure in place of "bf16 / 2"."""
+    import ctypes as C
+    from pde_policylearning_b200 import _lib
+    L = _lib.lib()
+    out = {}
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for name, kind in (("tf32", 0), ("bf16", 1)):
+        flops = C.c_double(0.0)
+        best = None
+        for _ in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(L.b2no_tc_peak_probe(kind, 20000, C.byref(flops), st), "tc_peak_probe")
+            e1.record()
+            torch.cuda.synchronize()
+            t = e0.elapsed_time(e1) * 1e-3
+            best = t if best is None else min(best, t)
+        out[name] = flops.value / best / 1e12
+    return out
+
+
 def kernel_probes(dev, hbm_peak_gbs, tf32_peak_tflops):
     """Times every hot kernel group of one training step at the workload's shape, each alone, with CUDA events on
     the launching stream, rotating over 3 buffer sets (working set > 126 MB L2).  Algorithmic bytes / flops per
-    launch are SURVEY.md 8d's formulas."""
+    launch are SURVEY.md 8d's formulas; the roofline fraction of a kernel is 8d's
+    max(bytes / HBM, p * flops / TC) / t with p = 3 (every product is issued three times: 3xTF32)."""
     from pde_policylearning_b200 import ops
     B, C, N, H = BATCH, WIDTH, GRID, 256
     geom = ops.SpecGeom(nin=(N, N), half=(MODES // 2, MODES // 2), norm="forward")
@@ -234,24 +259,195 @@ def kernel_probes(dev, hbm_peak_gbs, tf32_peak_tflops):
         dict(kernel="1x1 weight gradient (k_wgrad_tc + reduce)", fn=wgrad, bound="hbm", bytes=2 * bx, n=4),
         dict(kernel="projection head forward (k_mlp_tc<fwd>)", fn=head_fwd, bound="tensor", bytes=bx + px * 4,
              flops=2.0 * px * (C * H + H), n=1),
-        dict(kernel="projection head backward (k_mlp_tc<bwd>, gz written)", fn=head_bwd, bound="tensor",
-             bytes=2 * bx + px * 4 + px * H * 4, flops=2.0 * px * (2 * C * H + H), n=1),
+        # algorithmic bytes: read x, read g, write gx -- the 256-wide hidden tensor (and its gradient gz) is NOT
+        # algorithmic traffic ("the 256-wide hidden never touches HBM")
+        dict(kernel="projection head backward (k_mlp_tc<bwd>)", fn=head_bwd, bound="tensor",
+             bytes=2 * bx + px * 4, flops=2.0 * px * (2 * C * H + H), n=1),
     ]
+    # flops of the SpectralConv stages (DFT-as-GEMM model of SURVEY 8d), so that the same formula applies to every row
+    fl_w = 2.0 * B * C * N * N * 2 * (MODES // 2)               # last-dim real -> complex stage
+    fl_h = 8.0 * B * C * (MODES // 2) * N * MODES               # second stage, complex
+    for p, f in zip(probes[:4], (fl_w + fl_h, fl_w + fl_h + 2.0 * px * C * C, fl_w + fl_h + 2.0 * px * C * C,
+                                 fl_w + fl_h + 2.0 * px * C * C)):
+        p["flops"] = f
+    probes[4]["flops"] = 2.0 * px * C * C
     for p in probes:
         t = _time_op(p.pop("fn"))
         p["seconds"] = t
         p["launches_per_step"] = p.pop("n")
         p["gbs"] = p["bytes"] / t / 1e9
         p["hbm_frac"] = p["gbs"] / hbm_peak_gbs
-        if "flops" in p:
-            # algorithmic flops (each product counted once; the fp32-accurate 3xTF32 mode issues it three times)
-            p["tflops"] = p["flops"] / t / 1e12
-            p["tensor_frac"] = p["tflops"] / tf32_peak_tflops
-            p["tensor_frac_3xtf32_issue"] = 3.0 * p["tensor_frac"]
-        # the binding roof is the one the kernel sits closest to
-        p["bound"] = "tensor" if p.get("tensor_frac", 0.0) > p["hbm_frac"] else "hbm"
-        p["frac"] = max(p.get("tensor_frac", 0.0), p["hbm_frac"])
+        # algorithmic flops (each product counted once); p = 3 issues per product in the fp32-accurate 3xTF32 mode
+        p["tflops"] = p["flops"] / t / 1e12
+        p["issue_factor_p"] = 3
+        p["tensor_frac"] = 3.0 * p["tflops"] / tf32_peak_tflops
+        # the binding roof is the larger of the two ideal times
+        p["bound"] = "tensor" if p["tensor_frac"] > p["hbm_frac"] else "hbm"
+        p["frac"] = max(p["tensor_frac"], p["hbm_frac"])
     return probes
+
+
+
+# ---------------------------------------------------------------------------------------------
+# the other BASELINE configs: cfg3 (RNO training), cfg4 (PINO training), cfg5 (RNO control rollout)
+# ---------------------------------------------------------------------------------------------
+def _grf(shape_lead, n, seed, device):
+    """Smooth Gaussian random planes (.., n, n), unit variance per plane (channel-flow wall-pressure-like)."""
+    g = torch.Generator().manual_seed(seed)
+    k = torch.fft.fftfreq(n, 1.0 / n)
+    amp = (k[:, None] ** 2 + k[None, :] ** 2 + 49.0) ** (-1.25)
+    f = torch.fft.ifft2(torch.view_as_complex(torch.randn(*shape_lead, n, n, 2, generator=g)) * amp).real
+    return (f / f.std(dim=(-2, -1), keepdim=True)).float().to(device)
+
+
+def bench_cfg3(dev, rank, world, timed, steps=3, warmup=2, B=None, T=None, graph=True):
+    """cfg3: RNO observer (configs/matlab_rno.yaml: modes 12, width 34, layer_num 1, 32x32), trajectories of T = 100 frames,
+    batch 256 per GPU; step = forward (199 recurrent cell steps + 100 regressor calls), rel-L2 loss, backward through time,
+    (N > 1: NCCL gradient all-reduce), fused Adam.  `.eval()`: the regressor's dropout(0.3) is off, as in the parity tests."""
+    import pde_policylearning_b200 as P
+    B = int(os.environ.get("B2NO_CFG3_B", B or 256))
+    T = int(os.environ.get("B2NO_CFG3_T", T or 100))
+    torch.manual_seed(0)
+    model = P.RNO2dObserver(12, 12, 34, 0, layer_num=1).to(dev).eval()
+    x = _grf((B, T), 32, 300 + rank, dev).unsqueeze(-1)
+    tgt = _grf((B,), 32, 400 + rank, dev).unsqueeze(-1)
+    opt = P.FusedAdam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    lf = lambda o, t: P.rel_l2_loss(o.reshape(B, -1), t.reshape(B, -1), size_average=False)
+
+    def eager():
+        opt.zero_grad(set_to_none=True)
+        loss = lf(model(x), tgt)
+        loss.backward()
+        opt.sync_grads()
+        opt.step(grad_scale=1.0 / world)
+        return loss.detach()
+
+    gstep, mode = None, "eager"
+    if graph:
+        try:
+            gstep = P.GraphedTrainStep(model, lf, opt, (x,), tgt, warmup=1)
+            mode = f"one CUDA graph ({gstep.launches_per_step} library launches per step)"
+        except Exception as e:  # noqa: BLE001
+            print(f"warning: cfg3 graph capture failed ({type(e).__name__}: {e}); eager", file=sys.stderr)
+            gstep = None
+    fn = (lambda: gstep((x,), tgt)) if gstep is not None else eager
+    for _ in range(warmup):
+        fn()
+    ms = timed(fn, steps) / steps
+    peak_mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    if gstep is not None:
+        gstep.close()
+    convs = 8 * (2 * T - 1) + 2 * T
+    # SURVEY 8d per-conv algorithmic bytes at B = 256: fwd 74.0 MB, bwd 96.7 MB (scaled linearly in B)
+    alg_bytes = convs * (74.0e6 + 96.7e6) * B / 256.0
+    return {"config": "cfg3", "workload": f"RNO2dObserver(12,12,34,layer_num=1) 32x32, T={T} frames, batch {B} per GPU, fp32, "
+                                          "step = fwd + rel-L2 + BPTT + Adam, regressor dropout off (.eval())",
+            "metric": "rno_fwd_bwd_trajectories_per_s", "value": round(B * world / (ms * 1e-3), 2), "unit": "trajectories/s",
+            "ms_per_step": round(ms, 3), "ms_per_recurrent_step": round(ms / T, 4), "batch_per_gpu": B, "T": T, "n_gpus": world,
+            "spectral_conv_calls_per_step": convs, "execution": mode, "peak_mem_gib": round(peak_mem, 1),
+            "roofline": {"bound": "hbm", "algorithmic_bytes_per_step": alg_bytes, "unit": "GB/s",
+                         "achieved": round(alg_bytes / (ms * 1e-3) / 1e9, 1),
+                         "note": "whole step against HBM: spectral-conv calls x SURVEY 8d's per-conv fwd+bwd bytes / step time"}}
+
+
+def bench_cfg4(dev, rank, world, timed, steps=5, warmup=3, B=None):
+    """cfg4: PINObserver2d (pino-observer-pretrain-1s.yaml: 4 layers x 64 ch, modes 8, fc 128, pad 0.0625) on a 64x64x65
+    space-time grid, batch 4 per GPU; step = forward, 5 data + 1 f + 1 ic loss (train_pino.py:87-107), backward,
+    (N > 1: NCCL all-reduce of 269 MB of gradients), fused Adam."""
+    import pde_policylearning_b200 as P
+    B = int(os.environ.get("B2NO_CFG4_B", B or 4))
+    S, T = 64, 65
+    torch.manual_seed(0)
+    model = P.PINObserver2d(modes1=[8] * 4, modes2=[8] * 4, modes3=[8] * 4, fc_dim=128, layers=[64] * 5, act="gelu",
+                            pad_ratio=0.0625).to(dev)
+    a0 = _grf((B,), S, 500 + rank, dev)
+    gx = torch.linspace(0, 1, S + 1, device=dev)[:-1]
+    gt = torch.linspace(0, 1, T, device=dev)
+    a_in = torch.stack((gx.reshape(1, S, 1, 1).expand(B, S, S, T), gx.reshape(1, 1, S, 1).expand(B, S, S, T),
+                        gt.reshape(1, 1, 1, T).expand(B, S, S, T), a0.unsqueeze(-1).expand(B, S, S, T)), dim=-1).contiguous()
+    u = (a0.unsqueeze(-1) * torch.cos(gt * 3.0).reshape(1, 1, 1, T)).contiguous()
+    re = (torch.randint(100, 501, (B,), generator=torch.Generator().manual_seed(600 + rank)).float()).to(dev)
+    forcing = P.get_forcing(S, device=dev)
+    opt = P.FusedAdam(model.parameters(), lr=1e-3)
+    mode = os.environ.get("B2NO_CFG4_MODE", "fp32")
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = P.pino_training_loss(model, a_in, re, u, forcing, xy_weight=5.0, f_weight=1.0, ic_weight=1.0, t_interval=0.5)
+        loss.backward()
+        opt.sync_grads()
+        opt.step(grad_scale=1.0 / world)
+        return loss.detach()
+
+    for _ in range(warmup):
+        step()
+    ms = timed(step, steps) / steps
+    px = S * S * 73
+    alg_bytes = B * 4 * (679.5e6 + 750.8e6) / 4.0     # SURVEY 8d: per conv fwd 679.5 MB, bwd 750.8 MB at B = 4, four layers
+    return {"config": "cfg4", "workload": f"PINObserver2d 4x64ch modes 8 on 64x64x65 (padded to 73), batch {B} per GPU, step = fwd + "
+                                          "(5 data + f + ic) loss + bwd + Adam; the reference's second identical forward (train_pino.py:98, "
+                                          "quirk Q6) is computed once",
+            "metric": "pino_fwd_bwd_samples_per_s", "value": round(B * world / (ms * 1e-3), 2), "unit": "samples/s",
+            "ms_per_step": round(ms, 3), "batch_per_gpu": B, "n_gpus": world, "precision_mode": mode, "execution": "eager",
+            "grad_allreduce_bytes": int(sum((2 if p.is_complex() else 1) * p.numel() for p in model.parameters()) * 4),
+            "roofline": {"bound": "hbm", "algorithmic_bytes_per_step": alg_bytes, "unit": "GB/s",
+                         "achieved": round(alg_bytes / (ms * 1e-3) / 1e9, 1),
+                         "note": "four SpectralConv3d layers fwd+bwd (SURVEY 8d bytes) / whole step time, pointwise head / tail and "
+                                 "loss traffic not counted"}}
+
+
+def bench_cfg5(dev, rank, world, timed, steps=20, warmup=5, B=None):
+    """cfg5: batched control rollout -- the RNO observer called once per control step on B environments (run_control.py:150-151
+    batched), no_grad, .eval(); the environment is a stub that emits GRF pressure planes.  128 environments per GPU
+    (1024 over 8 GPUs); the single-GPU figure for all 1024 is reported next to it."""
+    import pde_policylearning_b200 as P
+    torch.manual_seed(0)
+    model = P.RNO2dObserver(12, 12, 34, 0, layer_num=1).to(dev).eval()
+    res = {}
+    for tag, Bn in (("per_gpu_128", int(os.environ.get("B2NO_CFG5_B", B or 128))), ("single_gpu_1024", 1024)):
+        x = _grf((Bn, 1), 32, 700 + rank, dev).unsqueeze(-1)
+        with torch.no_grad():
+            for _ in range(3):
+                out = model(x)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(g):
+                    out = model(x)
+                fn = g.replay
+                mode = "CUDA graph"
+            except Exception as e:  # noqa: BLE001
+                print(f"warning: cfg5 graph capture failed ({type(e).__name__}: {e}); eager", file=sys.stderr)
+                fn = lambda: model(x)
+                mode = "eager"
+            for _ in range(warmup):
+                fn()
+            ms = timed(fn, steps) / steps
+        res[tag] = {"envs": Bn, "ms_per_control_step": round(ms, 4), "env_steps_per_s": round(Bn / (ms * 1e-3), 1), "execution": mode}
+        del g
+    r = res["per_gpu_128"]
+    return {"config": "cfg5", "workload": "RNO2dObserver(12,12,34,layer_num=1) inference per control step on batched synthetic "
+                                          "environments (32x32 pressure planes), no_grad, 128 environments per GPU",
+            "metric": "rno_rollout_env_steps_per_s", "value": round(r["env_steps_per_s"] * world, 1), "unit": "env-steps/s",
+            "ms_per_step": r["ms_per_control_step"], "n_gpus": world, "detail": res}
+
+
+def other_configs(dev, rank, world, timed, args):
+    out = []
+    for name, fn in (("cfg3", bench_cfg3), ("cfg4", bench_cfg4), ("cfg5", bench_cfg5)):
+        if args.only and args.only != name:
+            continue
+        t0 = time.perf_counter()
+        try:
+            r = fn(dev, rank, world, timed)
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            r = {"config": name, "error": f"{type(e).__name__}: {e}"[:300]}
+        r["wall_s"] = round(time.perf_counter() - t0, 1)
+        out.append(r)
+        torch.cuda.empty_cache()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -265,6 +461,33 @@ def run_b200(args):
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    if args.only:
+        res = other_configs(dev, rank, world, timed, args)
+        if rank == 0:
+            emit(json.dumps(res[0]))
+        if world > 1:
+            dist.barrier()
+            os._exit(0)
+        return
+
     torch.manual_seed(0)                                    # identical weights on every rank
     model = P.FNO2dObserver(MODES, MODES, WIDTH).to(dev)
     lp = P.LpLoss(size_average=False)
@@ -294,24 +517,6 @@ def run_b200(args):
 
     def step(p, t):
         return graphed((p,), t) if graphed is not None else eager_step(p, t)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
 
     # resident inputs: the graph's static buffers already hold this rank's batch -> no copies in the timed region
     res_in = (graphed.static_in[0], graphed.static_tgt) if graphed is not None else (p_dev, t_dev)
@@ -365,9 +570,16 @@ def run_b200(args):
             pass
         hbm = float(peaks.get("hbm_gbs", 6650.0))
         bf16 = float(peaks.get("bf16_tflops", 1590.0))
-        tf32 = bf16 / 2.0
-        peak_src = ("measured (MEASURED_PEAKS.json: hbm_gbs; TF32 peak taken as bf16_tflops burst / 2, the datasheet ratio)"
-                    if "hbm_gbs" in peaks else "fallback 6650 GB/s, 1590 TFLOP/s bf16 / 2")
+        tcp = {}
+        try:
+            tcp = measured_tc_peaks(dev)
+        except Exception as e:  # noqa: BLE001
+            print(f"warning: tcgen05 peak probe failed ({e}); TF32 peak taken as bf16 / 2", file=sys.stderr)
+        tf32 = float(tcp.get("tf32", bf16 / 2.0))
+        peak_src = (("HBM: measured (MEASURED_PEAKS.json hbm_gbs); " if "hbm_gbs" in peaks else "HBM: fallback 6650 GB/s; ")
+                    + (f"tensor: kind::tf32 dense tcgen05.mma rate measured in this run by csrc/tc_peak.cu = {tf32:.0f} TFLOP/s "
+                       f"(kind::f16 bf16: {tcp.get('bf16', 0.0):.0f}; cuBLAS bf16 in MEASURED_PEAKS.json: {bf16:.0f})"
+                       if tcp else "tensor: bf16_tflops / 2 (probe unavailable)"))
         probes = kernel_probes(dev, hbm, tf32)
         for p in probes:
             p["share_of_step"] = p["seconds"] * p["launches_per_step"] / (ms_per_step * 1e-3)
@@ -378,10 +590,11 @@ def run_b200(args):
         except Exception:
             pass
         if top["bound"] == "tensor":
-            roofline = {"bound": "tensor", "kernel": top["kernel"], "achieved": round(top["tflops"], 2), "peak": tf32,
+            roofline = {"bound": "tensor", "kernel": top["kernel"], "achieved": round(3.0 * top["tflops"], 2), "peak": round(tf32, 1),
                         "unit": "TFLOP/s", "frac": round(top["frac"], 4), "traffic": traffic,
-                        "note": "achieved = algorithmic flops (each product once; 3xTF32 issues it three times) / launch time",
-                        "algorithmic_flops_per_launch": top["flops"]}
+                        "note": "SURVEY 8d: frac = max(bytes / HBM, p * flops / TC) / t; achieved = p * algorithmic flops / launch "
+                                "time with p = 3 (3xTF32 issues every product three times)",
+                        "algorithmic_flops_per_launch": top["flops"], "issue_factor_p": 3}
         else:
             roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": round(top["gbs"], 1), "peak": hbm,
                         "unit": "GB/s", "frac": round(top["frac"], 4), "traffic": traffic}
@@ -389,7 +602,8 @@ def run_b200(args):
                          "avg_launch_us": round(top["seconds"] * 1e6, 2),
                          "all": [{k: (round(v, 7 if k == "seconds" else 4) if isinstance(v, float) else v) for k, v in p.items()}
                                  for p in probes]})
-        cpu = cpu_reference_run(steps=20, warmup=2, sample_batch=16)     # ~10 s of host work: a bounded sample of the step
+        # the CPU leg runs at N = 1 only: at N > 1 the other ranks would spin in the next barrier on the same host cores
+        cpu = cpu_reference_run(steps=20, warmup=2, sample_batch=16) if world == 1 else None   # ~10 s of host work
         cfg = config_dict(world)
         cfg["cuda_graph"] = graphed is not None
         cfg["optimizer"] = "fused flat Adam (lr 1e-3, weight_decay 1e-4), inside the timed step"
@@ -397,8 +611,21 @@ def run_b200(args):
                "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-               "roofline": roofline, "cpu_baseline": cpu}
+               "roofline": roofline}
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+    # ---- the other BASELINE configs (cfg3 RNO training, cfg4 PINO training, cfg5 RNO control rollout), every rank ----
+    others = None
+    if not args.no_other:
+        if graphed is not None:
+            graphed.close()
+            graphed = None
+        del model, opt
+        torch.cuda.empty_cache()
+        others = other_configs(dev, rank, world, timed, args)
     if out is not None:
+        if others is not None:
+            out["other_configs"] = others
         emit(json.dumps(out))
     if world > 1:
         # tear down: the captured graph holds NCCL work, and destroying the communicator under a live graph blocks
@@ -463,6 +690,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--quick", action="store_true", help="device-timed value only (no e2e, probes or CPU baseline): A/B runs")
     ap.add_argument("--no-graph", action="store_true", help="run the training step eagerly instead of as one CUDA graph")
+    ap.add_argument("--no-other", action="store_true", help="skip the cfg3 / cfg4 / cfg5 measurements (other_configs)")
+    ap.add_argument("--only", default=None, choices=["cfg3", "cfg4", "cfg5"], help="measure one of the other configs alone")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

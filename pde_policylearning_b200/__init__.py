@@ -11,9 +11,10 @@ from .modules import (  # noqa: F401
     FactorizedSpectralConv, FactorizedSpectralConv1d, FactorizedSpectralConv2d, FactorizedSpectralConv3d,
     Lifting, Projection, FNOBlocks, FNO, FNO1d, FNO2d, FNO3d, FNO2dObserver, LpLoss,
     RnoSpectralConv2d, FourierLayer2d, RNO_cell, RNO_layer, SpectralConvWithFC, SpectralRegressor, RNO2d,
-    RNO2dObserver, PinoSpectralConv3d, MultiplicativeNet, PINObserver2d,
+    RNO2dObserver, PinoSpectralConv3d, MultiplicativeNet, PINObserver2d, PlanePredHead, PINObserverFullField,
+    PolicyModel2D, PinoSpectralConv2d, PinoFNO2d,
 )
-from .pino_loss import channelflow_pino_loss, fdm_ns_vorticity, get_forcing  # noqa: F401
+from .pino_loss import channelflow_pino_loss, fdm_ns_vorticity, get_forcing, pino_training_loss  # noqa: F401
 from .convert import convert_  # noqa: F401
 from .optim import FusedAdam, GraphedTrainStep, HostBatchPipeline  # noqa: F401
 

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # B2NO_LIB: load another build of the same sources (A/B measurements of compile-time switches)
 LIB_PATH = os.environ.get("B2NO_LIB") or os.path.join(_HERE, "libb2no.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["plan.cu", "spectral.cu", "pointwise.cu", "tc_pointwise.cu", "tc_wgrad.cu", "tc_mlp.cu", "tc_dft.cu", "tc_peak.cu", "optim.cu"]
+SOURCES = ["plan.cu", "spectral.cu", "pointwise.cu", "tc_pointwise.cu", "tc_wgrad.cu", "tc_mlp.cu", "tc_dft.cu", "tc_mix.cu", "tc_peak.cu", "optim.cu"]
 
 MAX_DIM = 3
 NORM = {"backward": 0, "forward": 1, "ortho": 2}

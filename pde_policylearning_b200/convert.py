@@ -6,6 +6,7 @@ Recognised by class name + parameter layout (no import of the reference is neede
   * FactorizedSpectralConv{,1d,2d,3d}  (neuralop/models/spectral_convolution.py)  -> SpectralConv
   * SpectralConv2d with ``fourier_weight`` (neuralop/models/rno.py:34-77)          -> RnoSpectralConv2d
   * SpectralConv3d with ``weights1..4``   (libs/models/pino_models/basics.py:99)   -> PinoSpectralConv3d
+  * SpectralConv2d with ``weights1..2``   (libs/models/pino_models/basics.py:64)   -> PinoSpectralConv2d
 With fuse=True the enclosing FNOBlocks / FourierLayer2d / Lifting / Projection are swapped as well so that the
 skip, bias and activation run in the fused epilogue instead of separate PyTorch ops.
 """
@@ -56,6 +57,16 @@ def _convert_pino_conv(ref) -> nn.Module:
         setattr(new, k, getattr(ref, k))
     for k in range(1, 5):
         setattr(new, f"weights{k}", getattr(ref, f"weights{k}"))
+    new.train(ref.training)
+    return new
+
+
+def _convert_pino_conv2d(ref) -> nn.Module:
+    new = M.PinoSpectralConv2d.__new__(M.PinoSpectralConv2d)
+    nn.Module.__init__(new)
+    for k in ("in_channels", "out_channels", "modes1", "modes2", "scale"):
+        setattr(new, k, getattr(ref, k))
+    new.weights1, new.weights2 = ref.weights1, ref.weights2
     new.train(ref.training)
     return new
 
@@ -134,6 +145,9 @@ def _swap(mod: nn.Module, fuse: bool):
         return _convert_rno_conv(mod)
     if name == "SpectralConv3d" and all(hasattr(mod, f"weights{k}") for k in range(1, 5)):
         return _convert_pino_conv(mod)
+    if (name == "SpectralConv2d" and hasattr(mod, "weights1") and hasattr(mod, "weights2") and not hasattr(mod, "weights3")
+            and getattr(mod.weights1, "is_complex", lambda: False)() and mod.weights1.dim() == 4):
+        return _convert_pino_conv2d(mod)                      # libs/models/pino_models/basics.py:64-96
     if fuse:
         if name == "FNOBlocks" and hasattr(mod, "fno_skips"):
             return _convert_fno_blocks(mod)

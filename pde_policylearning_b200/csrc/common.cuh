@@ -65,6 +65,56 @@ struct b2no_plan {
   int* row_local[2];    // [K_j] index inside the corner's weight
 };
 
+// ---- kept-mode bookkeeping shared by the mixing kernels (spectral.cu, tc_mix.cu) -----------------------------------
+// A flattened kept-mode index k (over K_0 x .. x K_{d-1}, last fastest) -> the corner weight tensor that holds it and
+// the offset inside that tensor (complex elements), following the corner convention of b2no_weights.
+struct ModeMap {
+  const int* corner[2];
+  const int* local[2];
+  int K[3];
+  int ndim;
+};
+
+__device__ __forceinline__ void decode_mode(const ModeMap& mm, const b2no_weights& w, int k, int* corner,
+                                            long* woff) {
+  int c = 0;
+  long off = 0;
+  const int d = mm.ndim;
+  int rem = k;
+  int idx[3] = {0, 0, 0};
+  for (int j = d - 1; j >= 0; j--) {
+    idx[j] = rem % mm.K[j];
+    rem /= mm.K[j];
+  }
+  for (int j = 0; j < d - 1; j++) {
+    c = c * 2 + mm.corner[j][idx[j]];
+    off += (long)mm.local[j][idx[j]] * w.stride_k[j];
+  }
+  off += (long)idx[d - 1] * w.stride_k[d - 1];
+  *corner = c;
+  *woff = off;
+}
+
+static inline ModeMap make_mode_map(const b2no_plan* p) {
+  ModeMap mm;
+  mm.ndim = p->g.ndim;
+  for (int j = 0; j < 3; j++) mm.K[j] = j < p->g.ndim ? p->K[j] : 1;
+  for (int j = 0; j < 2; j++) { mm.corner[j] = p->row_corner[j]; mm.local[j] = p->row_local[j]; }
+  return mm;
+}
+
+static inline int total_modes(const b2no_plan* p) {
+  int kt = 1;
+  for (int j = 0; j < p->g.ndim; j++) kt *= p->K[j];
+  return kt;
+}
+
+// tensor-core per-mode mixing (tc_mix.cu): return 0 = ran, 1 = shape not eligible (caller uses the CUDA-core kernel)
+int b2no_tc_mix(const b2no_plan* p, int mode, const float* in, const b2no_weights* w, float* out, int batch, int ci, int co,
+                int accumulate, cudaStream_t st);
+int b2no_tc_mix_dw(const b2no_plan* p, const float* xh, const float* gyh, const b2no_weights* dw, int batch, int ci, int co,
+                   int accumulate, cudaStream_t st);
+
 // ---- activations (exact forms: F.gelu default is the erf form) ---------------------------------
 // erf(x) as a rational minimax x * P(x^2) / Q(x^2) on [-4, 4] (clamped; erf(4) = 1 - 1.5e-8): max abs error
 // 4.5e-7 against float64 erf, 13 FMA-pipe instructions + one reciprocal instead of the ~40 of erff().  The GELU

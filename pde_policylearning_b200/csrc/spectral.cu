@@ -207,34 +207,6 @@ extern "C" int b2no_dft_forward(const b2no_plan* p, int which, const float* x, f
 // =============================================================================================
 // k_mix / k_dw
 // =============================================================================================
-struct ModeMap {
-  const int* corner[2];
-  const int* local[2];
-  int K[3];
-  int ndim;
-};
-
-__device__ __forceinline__ void decode_mode(const ModeMap& mm, const b2no_weights& w, int k, int* corner,
-                                            long* woff) {
-  // k flattened over (K_0, .., K_{d-1}), last fastest
-  int c = 0;
-  long off = 0;
-  const int d = mm.ndim;
-  int rem = k;
-  int idx[3] = {0, 0, 0};
-  for (int j = d - 1; j >= 0; j--) {
-    idx[j] = rem % mm.K[j];
-    rem /= mm.K[j];
-  }
-  for (int j = 0; j < d - 1; j++) {
-    c = c * 2 + mm.corner[j][idx[j]];
-    off += (long)mm.local[j][idx[j]] * w.stride_k[j];
-  }
-  off += (long)idx[d - 1] * w.stride_k[d - 1];
-  *corner = c;
-  *woff = off;
-}
-
 // out[b,p,k] (+)= sum_q in[b,q,k] * Wq    with  Wq = W[q,p,k] (CONJT=false)  or  conj(W[p,q,k]) (CONJT=true)
 template <int BT, int PT, bool CONJT>
 __global__ void __launch_bounds__(128)
@@ -373,26 +345,17 @@ k_dw2(const float2* __restrict__ xh, const float2* __restrict__ gyh, b2no_weight
   *dst = acc;
 }
 
-static ModeMap make_mode_map(const b2no_plan* p) {
-  ModeMap mm;
-  mm.ndim = p->g.ndim;
-  for (int j = 0; j < 3; j++) mm.K[j] = j < p->g.ndim ? p->K[j] : 1;
-  for (int j = 0; j < 2; j++) { mm.corner[j] = p->row_corner[j]; mm.local[j] = p->row_local[j]; }
-  return mm;
-}
-
-static int total_modes(const b2no_plan* p) {
-  int kt = 1;
-  for (int j = 0; j < p->g.ndim; j++) kt *= p->K[j];
-  return kt;
-}
-
 extern "C" int b2no_mix(const b2no_plan* p, int mode, const float* in, const b2no_weights* w, float* out,
                         int batch, int ci, int co, int accumulate, void* stream) {
   if (!p || !in || !w || !out || batch < 1 || ci < 1 || co < 1 || (mode != 0 && mode != 1)) return B2NO_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int Kt = total_modes(p);
   const ModeMap mm = make_mode_map(p);
+  {
+    // large batches: per-mode [batch x 2Cq] x [2Cq x 2Cp] real-block products on the tensor cores (tc_mix.cu)
+    const int rc = b2no_tc_mix(p, mode, in, w, out, batch, ci, co, accumulate, st);
+    if (rc != 1) return rc;
+  }
   const int Cq = mode == 0 ? ci : co, Cp = mode == 0 ? co : ci;
   const long total = (long)batch * Cp * Kt;
   const unsigned blocks = (unsigned)((total + 255) / 256);
@@ -455,6 +418,10 @@ extern "C" int b2no_mix_dw(const b2no_plan* p, const float* xh, const float* gyh
   cudaStream_t st = (cudaStream_t)stream;
   const int Kt = total_modes(p);
   const ModeMap mm = make_mode_map(p);
+  {
+    const int rc = b2no_tc_mix_dw(p, xh, gyh, dw, batch, ci, co, accumulate, st);
+    if (rc != 1) return rc;
+  }
   const long total = (long)ci * co * Kt;
   k_dw2<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float2*)xh, (const float2*)gyh, *dw, mm, batch, ci, co, Kt, accumulate);
   B2NO_LAUNCH_CHECK();

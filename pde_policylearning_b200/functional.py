@@ -324,6 +324,7 @@ class MlpHeadFn(torch.autograd.Function):
 def mlp_head(x, w1, b1, w2, b2, act="gelu"):
     """Projection head Ci -> hidden -> act -> 1 (tfno.py:34-38).  The fused kernels never materialise the hidden
     tensor in the forward; shapes without a fused kernel compose two pointwise convs (hidden saved for backward)."""
+    ops._require_cuda(x, w1, b1, w2, b2)
     needs_grad = torch.is_grad_enabled() and any(
         t is not None and t.requires_grad for t in (x, w1, b1, w2, b2))
     if (needs_grad and x.is_cuda and w2.reshape(-1, w1.shape[0]).shape[0] == 1 and (b1 is None or b1.dim() <= 2)
@@ -335,6 +336,10 @@ def mlp_head(x, w1, b1, w2, b2, act="gelu"):
         return ops.mlp_head_fwd(_contig(x.float()), _contig(w1.reshape(w1.shape[0], -1).float()),
                                 None if b1 is None else _contig(b1.float()), _contig(w2.reshape(-1).float()),
                                 None if b2 is None else _contig(b2.float()), act)
+    if b1 is not None and b1.dim() == 2:
+        # the composed path's epilogue reads bias[o] only: a (batch, hidden) bias would silently use sample 0's row
+        raise ValueError("mlp_head: a per-sample bias needs the fused head kernel (in_channels in {8, 16, 32, 64}, one output "
+                         "channel); pass the per-sample term as a 1-channel map through pointwise_conv2 instead")
     h = pointwise_conv(x, w1, b1, act)
     return pointwise_conv(h, w2, b2, None)
 
@@ -350,15 +355,21 @@ class RelL2Fn(torch.autograd.Function):
         xf, yf = _contig(x.float()).reshape(B, -1), _contig(y.float()).reshape(B, -1)
         sums = ops.rel_l2_sums(xf, yf)
         loss, coef = ops.rel_l2_finish(sums, bool(size_average))
-        ctx.save_for_backward(xf, yf, coef)
-        ctx.x_shape = tuple(x.shape)
+        ctx.save_for_backward(xf, yf, coef, sums)
+        ctx.x_shape, ctx.y_shape = tuple(x.shape), tuple(y.shape)
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        xf, yf, coef = ctx.saved_tensors
+        xf, yf, coef, sums = ctx.saved_tensors
         dx = ops.rel_l2_bwd_g(xf, yf, coef, _contig(g.float()))
-        return dx.reshape(ctx.x_shape), None, None
+        dy = None
+        if ctx.needs_input_grad[1]:
+            # LpLoss.rel is differentiable in the target too (libs/utilities3.py:323-334):
+            #   d/dy ||x-y|| / ||y|| = -(x-y) / (||x-y|| ||y||) - ||x-y|| y / ||y||^3 = -dx/g - coef (||x-y||^2 / ||y||^2) y
+            ratio = (g.float() * coef * sums[:, 0] / sums[:, 1]).reshape(-1, 1)
+            dy = (-dx - ratio * yf).reshape(ctx.y_shape)
+        return dx.reshape(ctx.x_shape), dy, None
 
 
 def rel_l2_loss(x, y, size_average=True):

@@ -801,19 +801,70 @@ class MultiplicativeNet(nn.Module):
 _PINO_ACTS = {"gelu": "gelu", "tanh": "tanh", "relu": "relu"}
 
 
+def _pino_trunk_forward(x, re, fc0, mnet1, sp_convs, ws, mnet2, fc1, fc2, act_name, pad_ratio):
+    """The PINO "FNO3d" trunk shared by PINObserver2d.forward (pinobserver.py:192-233), PlanePredHead.forward under
+    PINObserverFullField / PolicyModel2D (:257-273, :337-368, :433-463).  x: (B, X, Y, T, in_dim) channels-last, re: (B,) or
+    (B, 1) ALREADY scaled by the caller (the full-field / policy models divide by max_re, PINObserver2d does not).
+    Returns (B, X, Y, T, out_dim).
+
+    The pointwise head (fc0 + MultiplicativeNet1 + permute + pad) is folded into ONE 1x1 conv over the channels-first
+    input [x (in_dim), re, valid-mask]; every Fourier layer is one fused pass (spectral conv + Conv1d(k=1) + bias + act);
+    the tail (unpad + MultiplicativeNet2 + fc1 + act + fc2) runs on the padded grid with MultiplicativeNet2 folded into
+    fc1 and the Reynolds term entering as a per-sample bias (fused head kernel) or a 1-channel map."""
+    re = re.float()
+    B, sx, sy, sz, _ = x.shape
+    if max(pad_ratio) > 0:
+        num_pad = [round(sz * i) for i in pad_ratio]
+    else:
+        num_pad = [0, 0]
+    if re.dim() < 2:
+        re = re.unsqueeze(-1)
+    # ---- head: fold fc0 and MultiplicativeNet1 into one (C0 x (in_dim + 2)) 1x1 conv ----
+    w_in = mnet1.B @ fc0.weight                                   # (C0, in_dim)
+    b_in = mnet1.B @ fc0.bias + mnet1.bias                        # (C0,)
+    w6 = torch.cat([w_in, mnet1.A, b_in[:, None]], dim=1)         # (C0, in_dim + 2)
+    ones = torch.ones((B, sx, sy, sz, 1), dtype=x.dtype, device=x.device)
+    x6 = torch.cat([x, re.reshape(B, 1, 1, 1, 1).expand(B, sx, sy, sz, 1), ones], dim=-1)
+    x6 = x6.permute(0, 4, 1, 2, 3)
+    if max(num_pad) > 0:
+        x6 = F.pad(x6, (num_pad[0], num_pad[1]), "constant", 0)   # zero mask => padded output is exactly 0
+    h = Fn.pointwise_conv(x6.contiguous(), w6, None, None)
+    # ---- Fourier layers ----
+    L = len(ws)
+    for i, (conv, w) in enumerate(zip(sp_convs, ws)):
+        h = conv.forward_fused(h, bias=w.bias, pw_weight=w.weight, act=act_name if i != L - 1 else None)
+    # ---- tail: fold MultiplicativeNet2 into fc1; run on the padded grid, slice the result ----
+    w1 = fc1.weight @ mnet2.B                                     # (fc_dim, C)
+    wre = fc1.weight @ mnet2.A                                    # (fc_dim, 1)
+    b1 = fc1.weight @ mnet2.bias + fc1.bias                       # (fc_dim,)
+    szp = sz + num_pad[0] + num_pad[1]
+    no_grad = not (torch.is_grad_enabled() and (h.requires_grad or w1.requires_grad))
+    if no_grad and fc2.out_features == 1 and h.shape[1] in (8, 16, 32, 64):
+        # inference: fused head, per-sample bias carries the Reynolds term; hidden never materialised
+        out = Fn.mlp_head(h, w1, b1[None, :] + re @ wre.t(), fc2.weight, fc2.bias, act_name)
+    else:
+        re_map = re.reshape(B, 1, 1, 1, 1).expand(B, 1, sx, sy, szp).contiguous()
+        t = Fn.pointwise_conv2(h, w1, b1, act_name, re_map, wre)
+        out = Fn.pointwise_conv(t, fc2.weight, fc2.bias, None)    # (B, out_dim, sx, sy, szp)
+    if max(num_pad) > 0:
+        out = out[..., num_pad[0]: szp - num_pad[1]]
+    return out.permute(0, 2, 3, 4, 1)
+
+
+def _pad_pair(pad_ratio):
+    if isinstance(pad_ratio, float):
+        return [pad_ratio, pad_ratio]
+    assert len(pad_ratio) == 2, "Cannot add padding in more than 2 directions."
+    return pad_ratio
+
+
 class PINObserver2d(nn.Module):
-    """pinobserver.py:129-233.  The pointwise head (fc0 + MultiplicativeNet1 + permute + pad) is folded into
-    ONE 1x1 conv over a 6-channel channels-first input [a_in(4), re, valid-mask]; every Fourier layer is one
-    fused pass (spectral conv + Conv1d(k=1) + bias + GELU); the tail (unpad + MultiplicativeNet2 + fc1 + GELU
-    + fc2) is the projection-head kernel with the MultiplicativeNet folded into fc1."""
+    """pinobserver.py:129-233 (see _pino_trunk_forward for how the pointwise head / tail are folded)."""
 
     def __init__(self, modes1, modes2, modes3, width=16, fc_dim=128, layers=None, in_dim=4, out_dim=1,
                  act="gelu", pad_ratio=[0., 0.], use_fourier_layer=False):
         super().__init__()
-        if isinstance(pad_ratio, float):
-            pad_ratio = [pad_ratio, pad_ratio]
-        else:
-            assert len(pad_ratio) == 2, "Cannot add padding in more than 2 directions."
+        pad_ratio = _pad_pair(pad_ratio)
         if use_fourier_layer:
             raise NotImplementedError("native PINObserver2d: use_fourier_layer is outside the hot path")
         if act not in _PINO_ACTS:
@@ -835,42 +886,153 @@ class PINObserver2d(nn.Module):
         self.act_name = _PINO_ACTS[act]
 
     def forward(self, x, re):
-        re = re.float()
-        B, sx, sy, sz, _ = x.shape
-        if max(self.pad_ratio) > 0:
-            num_pad = [round(sz * i) for i in self.pad_ratio]
+        return _pino_trunk_forward(x, re, self.fc0, self.multiplicative_net1, self.sp_convs, self.ws,
+                                   self.multiplicative_net2, self.fc1, self.fc2, self.act_name, self.pad_ratio)
+
+
+class PlanePredHead(nn.Module):
+    """pinobserver.py:236-273: the Fourier layers + fc1 / fc2 of one prediction head (parameters only; the arithmetic is
+    _pino_trunk_forward, driven by the owning PINObserverFullField / PolicyModel2D)."""
+
+    def __init__(self, layers, modes1, modes2, modes3, fc_dim, out_dim, act):
+        super().__init__()
+        if act not in _PINO_ACTS:
+            raise NotImplementedError(f"native PlanePredHead: act={act!r} has no kernel")
+        self.layers, self.modes1, self.modes2, self.modes3 = layers, modes1, modes2, modes3
+        self.sp_convs = nn.ModuleList([PinoSpectralConv3d(i, o, m1, m2, m3) for i, o, m1, m2, m3 in
+                                       zip(self.layers, self.layers[1:], modes1, modes2, modes3)])
+        self.ws = nn.ModuleList([nn.Conv1d(i, o, 1) for i, o in zip(self.layers, self.layers[1:])])
+        self.fc1 = nn.Linear(layers[-1], fc_dim)
+        self.fc2 = nn.Linear(fc_dim, out_dim)
+        self.act_name = _PINO_ACTS[act]
+
+
+class _PinoHeadedModel(nn.Module):
+    """Shared constructor of PINObserverFullField / PolicyModel2D (pinobserver.py:276-331, 378-433)."""
+
+    def _build(self, head_name, head_out_dim, modes1, modes2, modes3, width, fc_dim, layers, in_dim, act, pad_ratio,
+               use_fourier_layer):
+        if use_fourier_layer:
+            raise NotImplementedError(f"native {type(self).__name__}: use_fourier_layer is outside the hot path")
+        self.pad_ratio = _pad_pair(pad_ratio)
+        self.modes1, self.modes2, self.modes3 = modes1, modes2, modes3
+        self.max_re = 1000
+        self.in_dim = in_dim
+        self.layers = [width] * 4 if layers is None else layers
+        self.fc0 = nn.Linear(in_dim, self.layers[0])
+        self.use_fourier_layer = False
+        self.fourier_layer1 = None
+        self.multiplicative_net1 = MultiplicativeNet(self.layers[0], 1, self.layers[0])
+        self.multiplicative_net2 = MultiplicativeNet(self.layers[-1], 1, self.layers[-1])
+        setattr(self, head_name, PlanePredHead(self.layers, modes1, modes2, modes3, fc_dim, head_out_dim, act))
+
+    def _trunk(self, head, x, re):
+        return _pino_trunk_forward(x, re.float() / self.max_re, self.fc0, self.multiplicative_net1, head.sp_convs, head.ws,
+                                   self.multiplicative_net2, head.fc1, head.fc2, head.act_name, self.pad_ratio)
+
+
+class PINObserverFullField(_PinoHeadedModel):
+    """pinobserver.py:276-375: the shared trunk with ONE head emitting plane_num * out_dim channels; re / max_re."""
+
+    def __init__(self, plane_num, modes1, modes2, modes3, width=16, fc_dim=128, layers=None, in_dim=4, out_dim=1,
+                 act="gelu", pad_ratio=[0., 0.], use_fourier_layer=False):
+        super().__init__()
+        self.plane_num = plane_num
+        self._build("observer_head", out_dim * plane_num, modes1, modes2, modes3, width, fc_dim, layers, in_dim, act,
+                    pad_ratio, use_fourier_layer)
+
+    def forward(self, x, re):
+        return self._trunk(self.observer_head, x, re).permute(0, 4, 1, 2, 3)      # (B, planes, X, Y, T)
+
+
+class PolicyModel2D(_PinoHeadedModel):
+    """pinobserver.py:378-463: the policy network of the gradient-through-observer control loop (run_control.py:162-185);
+    every parameter starts at zero (:432-433)."""
+
+    def __init__(self, modes1, modes2, modes3, width=16, fc_dim=128, layers=None, in_dim=4, out_dim=1, act="gelu",
+                 pad_ratio=[0., 0.], use_fourier_layer=False):
+        super().__init__()
+        self._build("pred_net", out_dim, modes1, modes2, modes3, width, fc_dim, layers, in_dim, act, pad_ratio,
+                    use_fourier_layer)
+        for param in self.parameters():
+            nn.init.zeros_(param)
+
+    def forward(self, x, re):
+        return self._trunk(self.pred_net, x, re)
+
+
+# ---------------------------------------------------------------------------------------------
+# libs/models/pino_models/{basics.SpectralConv2d, fourier2d.FNO2d}
+# ---------------------------------------------------------------------------------------------
+class PinoSpectralConv2d(nn.Module):
+    """basics.py:64-96: cfloat weights1 (low rows) / weights2 (high rows), un-halved modes, norm 'backward'."""
+
+    def __init__(self, in_channels, out_channels, modes1, modes2):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.modes1, self.modes2 = modes1, modes2
+        self.scale = 1 / (in_channels * out_channels)
+        for k in (1, 2):
+            setattr(self, f"weights{k}", nn.Parameter(
+                self.scale * torch.rand(in_channels, out_channels, modes1, modes2, dtype=torch.cfloat)))
+
+    def corners(self):
+        return [self.weights1, self.weights2]
+
+    def geom(self, grid) -> SpecGeom:
+        return SpecGeom(nin=tuple(grid), half=(self.modes1, self.modes2), norm="backward")
+
+    def forward(self, x):
+        return self.forward_fused(x)
+
+    def forward_fused(self, x, bias=None, pw_weight=None, act=None):
+        return Fn.spectral_block(x, self.corners(), self.geom(tuple(x.shape[2:])), bias=bias, pw_weight=pw_weight, act=act)
+
+
+class PinoFNO2d(nn.Module):
+    """libs/models/pino_models/fourier2d.py:6-87 (the class is called FNO2d there; exported here as PinoFNO2d because the
+    neuralop FNO2d of tfno.py has that name in this package).  fc0 -> two-sided zero padding of both axes -> n x (spectral
+    conv + Conv1d(k=1) + act, fused) -> unpad -> fc1, act, fc2, act, fc3."""
+
+    def __init__(self, modes1, modes2, width=64, fc_dim=128, layers=None, in_dim=3, out_dim=1, act="gelu",
+                 pad_ratio=[0., 0.]):
+        super().__init__()
+        if isinstance(pad_ratio, float):
+            pad_ratio = [pad_ratio, pad_ratio]
         else:
-            num_pad = [0, 0]
-        if re.dim() < 2:
-            re = re.unsqueeze(-1)
-        # ---- head: fold fc0 and MultiplicativeNet1 into one (C0 x 6) 1x1 conv ----
-        m1 = self.multiplicative_net1
-        w_in = m1.B @ self.fc0.weight                             # (C0, in_dim)
-        b_in = m1.B @ self.fc0.bias + m1.bias                     # (C0,)
-        w6 = torch.cat([w_in, m1.A, b_in[:, None]], dim=1)        # (C0, in_dim + 2)
-        ones = torch.ones((B, sx, sy, sz, 1), dtype=x.dtype, device=x.device)
-        x6 = torch.cat([x, re.reshape(B, 1, 1, 1, 1).expand(B, sx, sy, sz, 1), ones], dim=-1)
-        x6 = x6.permute(0, 4, 1, 2, 3)
-        if max(num_pad) > 0:
-            x6 = F.pad(x6, (num_pad[0], num_pad[1]), "constant", 0)  # zero mask => padded output is exactly 0
-        h = Fn.pointwise_conv(x6.contiguous(), w6, None, None)
-        # ---- Fourier layers ----
+            assert len(pad_ratio) == 2, "Cannot add padding in more than 2 directions"
+        if act not in _PINO_ACTS:
+            raise NotImplementedError(f"native PinoFNO2d: act={act!r} has no kernel")
+        self.modes1, self.modes2, self.pad_ratio = modes1, modes2, pad_ratio
+        self.layers = [width] * (len(modes1) + 1) if layers is None else layers
+        self.fc0 = nn.Linear(in_dim, self.layers[0])
+        self.sp_convs = nn.ModuleList([PinoSpectralConv2d(i, o, m1, m2) for i, o, m1, m2 in
+                                       zip(self.layers, self.layers[1:], modes1, modes2)])
+        self.ws = nn.ModuleList([nn.Conv1d(i, o, 1) for i, o in zip(self.layers, self.layers[1:])])
+        self.fc1 = nn.Linear(self.layers[-1], fc_dim)
+        self.fc2 = nn.Linear(fc_dim, self.layers[-1])
+        self.fc3 = nn.Linear(self.layers[-1], out_dim)
+        self.act_name = _PINO_ACTS[act]
+
+    def forward(self, x):
+        s1, s2 = x.shape[1], x.shape[2]
+        if max(self.pad_ratio) > 0:
+            p1 = [round(i * s1) for i in self.pad_ratio]
+            p2 = [round(i * s2) for i in self.pad_ratio]
+        else:
+            p1 = p2 = [0, 0]
+        h = Fn.pointwise_conv(x.permute(0, 3, 1, 2), self.fc0.weight, self.fc0.bias, None)
+        padded = max(p1) > 0 or max(p2) > 0
+        if padded:
+            h = F.pad(h, (p2[0], p2[1], p1[0], p1[1]), "constant", 0.)
         L = len(self.ws)
         for i, (conv, w) in enumerate(zip(self.sp_convs, self.ws)):
             h = conv.forward_fused(h, bias=w.bias, pw_weight=w.weight, act=self.act_name if i != L - 1 else None)
-        # ---- tail: fold MultiplicativeNet2 into fc1; run on the padded grid, slice the 1-channel result ----
-        m2 = self.multiplicative_net2
-        w1 = self.fc1.weight @ m2.B                                # (fc_dim, C)
-        wre = self.fc1.weight @ m2.A                               # (fc_dim, 1)
-        b1 = self.fc1.weight @ m2.bias + self.fc1.bias             # (fc_dim,)
-        szp = sz + num_pad[0] + num_pad[1]
-        if not (torch.is_grad_enabled() and (h.requires_grad or w1.requires_grad)) and self.fc2.out_features == 1:
-            # inference: fused head, per-sample bias carries the Reynolds term; hidden never materialised
-            out = Fn.mlp_head(h, w1, b1[None, :] + re @ wre.t(), self.fc2.weight, self.fc2.bias, self.act_name)
-        else:
-            re_map = re.reshape(B, 1, 1, 1, 1).expand(B, 1, sx, sy, szp).contiguous()
-            t = Fn.pointwise_conv2(h, w1, b1, self.act_name, re_map, wre)
-            out = Fn.pointwise_conv(t, self.fc2.weight, self.fc2.bias, None)   # (B, out_dim, sx, sy, szp)
-        if max(num_pad) > 0:
-            out = out[..., num_pad[0]: szp - num_pad[1]]
-        return out.permute(0, 2, 3, 4, 1)
+        if padded:
+            # remove_padding2 (utils.py:28-33) slices [p[0]:-p[1]]: with p[1] == 0 that is an EMPTY slice in the reference;
+            # mirrored literally so that a mis-configured pad_ratio fails the same way
+            h = h[..., p1[0]:-p1[1], p2[0]:-p2[1]]
+        h = Fn.pointwise_conv(h, self.fc1.weight, self.fc1.bias, self.act_name)
+        h = Fn.pointwise_conv(h, self.fc2.weight, self.fc2.bias, self.act_name)
+        h = Fn.pointwise_conv(h, self.fc3.weight, self.fc3.bias, None)
+        return h.permute(0, 2, 3, 1)

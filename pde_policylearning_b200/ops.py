@@ -34,10 +34,16 @@ def tensor_core_launches() -> int:
 
 def _require_cuda(*tensors):
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError(
                 "pde_policylearning_b200: the spectral-conv hot path runs only on CUDA (sm_100a); "
                 f"got a tensor on {t.device}.  There is no CPU fallback.")
+        if t.device.index != torch.cuda.current_device():
+            # launches go to the CURRENT device's current stream (one process per GPU: parallel.init_from_env sets it)
+            raise RuntimeError(f"pde_policylearning_b200: tensor on {t.device} but the current CUDA device is "
+                               f"cuda:{torch.cuda.current_device()}; call torch.cuda.set_device first")
 
 
 def _ptr(t: Optional[torch.Tensor]):

@@ -129,8 +129,14 @@ class GraphedTrainStep:
     def __call__(self, inputs, target):
         for dst, src in zip(self.static_in, inputs):
             if dst.data_ptr() != src.data_ptr():
+                if tuple(src.shape) != tuple(dst.shape):      # copy_ would broadcast a ragged last batch silently
+                    raise ValueError(f"GraphedTrainStep: input of shape {tuple(src.shape)}, the graph was captured for "
+                                     f"{tuple(dst.shape)}")
                 dst.copy_(src, non_blocking=True)
         if self.static_tgt.data_ptr() != target.data_ptr():
+            if tuple(target.shape) != tuple(self.static_tgt.shape):
+                raise ValueError(f"GraphedTrainStep: target of shape {tuple(target.shape)}, the graph was captured for "
+                                 f"{tuple(self.static_tgt.shape)}")
             self.static_tgt.copy_(target, non_blocking=True)
         self.graph.replay()
         ops._REPLAYED[0] += self.launches_per_step

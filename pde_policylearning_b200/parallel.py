@@ -104,6 +104,9 @@ class GradBucket:
             cnts = [(2 if p.is_complex() else 1) * p.numel() for p in self.params]
             self._seg_dev = (torch.tensor(offs, dtype=torch.int64, device=dev), torch.tensor(cnts, dtype=torch.int64, device=dev))
             self._ptr_dev = torch.zeros(nseg, dtype=torch.int64, device=dev)
+            # pinned host pointer tables, allocated ONCE (no cudaHostAlloc inside a CUDA-graph capture); two of them so
+            # that a table a captured graph copies from at every replay is never rewritten by a later eager call
+            self._ptr_host = [torch.zeros(nseg, dtype=torch.int64).pin_memory() for _ in range(2)]
             self._keep = []
         ptrs, keep, in_place = [], [], True
         for p, v in zip(self.params, views):
@@ -120,13 +123,18 @@ class GradBucket:
             ptrs.append(g.data_ptr())
             in_place = in_place and g.data_ptr() == v.data_ptr()
         if not in_place:
-            host = torch.tensor(ptrs, dtype=torch.int64).pin_memory()
             capturing = torch.cuda.is_current_stream_capturing()
-            # the host table must stay untouched for as long as a captured graph may replay the copy
-            (self._keep if capturing else keep).append(host)
+            # the host table must stay untouched for as long as a captured graph may replay the copy: captures own table 1
+            host = self._ptr_host[1 if capturing else 0]
+            if not capturing and getattr(self, "_host_copied", None) is not None:
+                self._host_copied.synchronize()          # the previous call's async copy out of this table has finished
+            host.copy_(torch.tensor(ptrs, dtype=torch.int64))
             if capturing:
                 self._keep.extend(keep)
             self._ptr_dev.copy_(host, non_blocking=True)
+            if not capturing:
+                self._host_copied = torch.cuda.Event()
+                self._host_copied.record(torch.cuda.current_stream(dev))
             ops.gather_segments(self.flat, self._ptr_dev, self._seg_dev[0], self._seg_dev[1], nseg)
             if not capturing:
                 # eager: the source tensors / host table may be freed once the copy + kernel are enqueued only because

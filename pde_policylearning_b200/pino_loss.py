@@ -114,3 +114,26 @@ def channelflow_pino_loss(model_output: torch.Tensor, u0: torch.Tensor, forcing:
     du = fdm_ns_vorticity(out, v, t_interval)
     f = forcing.expand(B, nx, ny, nt - 2)
     return loss_ic, _rel(du, f)
+
+
+def pino_training_loss(model, a_in: torch.Tensor, re: torch.Tensor, u: torch.Tensor, forcing: torch.Tensor,
+                       xy_weight: float = 5.0, f_weight: float = 1.0, ic_weight: float = 1.0,
+                       t_interval: float = 1.0) -> torch.Tensor:
+    """The loss of one PINO training iteration, train_pino.py:87-107:
+
+        loss = xy_weight * LpLoss(out, u) + f_weight * loss_f + ic_weight * loss_ic
+
+    The reference runs the model TWICE per iteration when both terms are on (train_pino.py:88 and :98, quirk Q6): same
+    weights, same input, no dropout -- the two outputs are the same tensor, so it is computed once here and both losses
+    (and both gradient contributions) use it."""
+    B, S1, S2, T = a_in.shape[:4]
+    out = model(a_in, re).reshape(B, S1, S2, T)
+    loss = None
+    if xy_weight > 0:
+        loss = xy_weight * _rel(out, u)
+    if f_weight != 0.0:
+        u0 = a_in[:, :, :, 0, -1]
+        loss_ic, loss_f = channelflow_pino_loss(out, u0, forcing, 1.0 / re, t_interval)
+        extra = f_weight * loss_f + ic_weight * loss_ic
+        loss = extra if loss is None else loss + extra
+    return loss

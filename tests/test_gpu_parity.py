@@ -632,3 +632,206 @@ def test_host_batch_pipeline_matches_direct_steps():
     s1.close()
     s2.close()
     s3.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: tensor-core mixing, gate epilogue, the regrouped RNO layer, launch-evidence assertions
+# ---------------------------------------------------------------------------------------------
+MIX_CASES = [
+    # grid, half, ci, co, batch, real-pair weights
+    ((32, 32), (12, 12), 34, 34, 256, True),      # cfg3 RNO conv
+    ((32, 32), (12, 12), 34, 68, 130, True),      # gate-stacked weights, ragged last tile
+    ((16, 16), (4, 5), 10, 3, 200, False),        # odd channel counts (padding rows / columns)
+    ((8, 8, 8), (2, 2, 3), 8, 8, 128, False),     # 3-D mode map (4 corners)
+    ((64,), (9,), 16, 24, 128, False),            # 1-D
+]
+
+
+@pytest.mark.parametrize("case", MIX_CASES, ids=lambda c: "x".join(map(str, c[0])) + f"-{c[2]}to{c[3]}-b{c[4]}")
+def test_tensor_core_mixing(case):
+    """tc_mix.cu through b2no_mix / b2no_mix_dw (large batch): Yh, its adjoint, dW (plain and accumulated) vs complex128,
+    on the tensor-core and the CUDA-core kernels."""
+    from oracle import closed_form as cf
+    from pde_policylearning_b200 import ops
+    grid, half, ci, co, B, pairs = case
+    dev = _dev()
+    torch.manual_seed(5)
+    g64 = cf.SpecGeom(nin=grid, half=half, norm="ortho")
+    plan = ops.get_plan(ops.SpecGeom(nin=grid, half=half, norm="ortho"), dev)
+    nc = 2 ** (len(grid) - 1)
+    corners = [torch.randn(ci, co, *half, dtype=torch.cfloat) for _ in range(nc)]
+    W = cf.gather_weight(g64, corners)
+    xh = torch.randn(B, ci, *plan.kept, dtype=torch.cfloat)
+    gyh = torch.randn(B, co, *plan.kept, dtype=torch.cfloat)
+    y64 = torch.einsum("bi...,io...->bo...", xh.to(torch.complex128), W)
+    gx64 = torch.einsum("bo...,io...->bi...", gyh.to(torch.complex128), W.conj())
+    dW64 = cf.scatter_weight_grad(g64, torch.einsum("bi...,bo...->io...", xh.to(torch.complex128).conj(), gyh.to(torch.complex128)),
+                                  [tuple(c.shape) for c in corners])
+    cd = [(torch.view_as_real(c).contiguous() if pairs else c).to(dev) for c in corners]
+    xhd, gyhd = xh.to(dev), gyh.to(dev)
+    try:
+        for mode in (True, False):
+            assert ops.set_tensor_core_mode(mode) == mode
+            n0 = ops.tensor_core_launches()
+            y = ops.mix(plan, 0, xhd, cd, ci, co)
+            gx = ops.mix(plan, 1, gyhd, cd, ci, co)
+            gx2 = ops.mix(plan, 1, gyhd, cd, ci, co, out=gx.clone(), accumulate=True)
+            dW = ops.mix_dw(plan, xhd, gyhd, cd, needs_zero=True)
+            acc = [d.clone() for d in dW]
+            ops.mix_dw(plan, xhd, gyhd, cd, needs_zero=False, out=acc, accumulate=True)
+            assert (ops.tensor_core_launches() - n0 == 5) == mode, "tensor-core mixing kernel did not run when expected"
+            as_c = lambda t: t if t.is_complex() else torch.view_as_complex(t.contiguous())
+            errs = [rel(y, y64), rel(gx, gx64), rel(gx2, 2 * gx64)] + [rel(as_c(d), r) for d, r in zip(dW, dW64)] \
+                + [rel(as_c(d), 2 * r) for d, r in zip(acc, dW64)]
+            assert max(errs) < TOL, (mode, errs)
+    finally:
+        ops.set_tensor_core_mode(True)
+
+
+def test_gate_epilogue_and_cell_backward_kernels():
+    """The GRU update of rno.py:259 as the inverse-transform epilogue (gate_z / gate_h / strided mul), on the tile kernel and
+    the CUDA-core kernel, and the two fused cell-backward kernels, vs float64."""
+    from oracle import closed_form as cf
+    from pde_policylearning_b200 import ops
+    dev = _dev()
+    torch.manual_seed(3)
+    B, C, n, m = 3, 34, 32, 12
+    g64 = cf.SpecGeom(nin=(n, n), half=(m, m), norm="ortho")
+    plan = ops.get_plan(ops.SpecGeom(nin=(n, n), half=(m, m), norm="ortho"), dev)
+    _, si = g64.scales()
+    yh = torch.randn(B, C, *plan.kept, dtype=torch.cfloat)
+    rh, h, add = torch.randn(B, C, n, n), torch.randn(B, C, n, n), torch.randn(B, C, n, n)
+    zz2 = torch.rand(B, 2 * C, n, n)
+    w = torch.randn(C, C) * 0.2
+    a64 = cf.idft_trunc(g64, yh.to(torch.complex128), si) + torch.einsum("oi,bi...->bo...", w.double(), rh.double()) + add.double()
+    hn64 = (1 - zz2[:, :C].double()) * h.double() + zz2[:, C:].double() * torch.nn.functional.selu(a64)
+    yhd, rhd, hd, addd, zd, wd = (t.to(dev) for t in (yh, rh, h, add, zz2, w))
+    try:
+        for mode in (True, False):
+            ops.set_tensor_core_mode(mode)
+            ah = torch.empty(B, C, n, n, device=dev)
+            hn = ops.dft_inverse(plan, 0, yhd, ops.make_epilogue(pw_w=wd, pw_x=rhd, add=addd, act="selu", preact=ah,
+                                                                mul=zd[:, C:], gate_z=zd[:, :C], gate_h=hd))
+            assert rel(ah, a64) < TOL and rel(hn, hn64) < TOL, (mode, rel(ah, a64), rel(hn, hn64))
+    finally:
+        ops.set_tensor_core_mode(True)
+    # fused backward kernels
+    g = torch.randn(B, C, n, n)
+    ahc = a64.float()
+    z, z2 = zz2[:, :C].double(), zz2[:, C:].double()
+    a = ahc.double().requires_grad_(True)
+    hh = torch.nn.functional.selu(a)
+    (dselu,) = torch.autograd.grad(hh.sum(), a)
+    g_zz2 = torch.empty(B, 2 * C, n, n, device=dev)
+    g_ah = torch.empty(B, C, n, n, device=dev)
+    g_h = ops.rno_cell_bwd(g.to(dev), hd, zd, ahc.to(dev), g_zz2, g_ah)
+    gd = g.double()
+    assert rel(g_zz2[:, :C], -gd * h.double() * z * (1 - z)) < TOL
+    assert rel(g_zz2[:, C:], gd * hh.detach() * z2 * (1 - z2)) < TOL
+    assert rel(g_ah, gd * z2 * dselu) < TOL and rel(g_h, gd * (1 - z)) < TOL
+    ar = torch.randn(B, C, n, n)
+    r = torch.sigmoid(ar.double())
+    g_ar = torch.empty(B, C, n, n, device=dev)
+    gh0 = torch.randn(B, C, n, n)
+    ghd = gh0.to(dev).clone()
+    ops.rno_reset_bwd(g.to(dev), hd, ar.to(dev), g_ar, ghd)
+    assert rel(g_ar, gd * h.double() * r * (1 - r)) < TOL and rel(ghd, gh0.double() + gd * r) < TOL
+
+
+def test_rno_layer_regrouped_vs_reference_composition():
+    """cfg3 layer shape (width 34, modes 12, 32x32), B = 128 so that the tensor-core mixing runs: the regrouped layer
+    (functional.RnoLayerFn) against autograd through the un-regrouped composition of the same kernels' FourierLayer2d
+    calls -- outputs, dx, dh0 and every parameter gradient."""
+    import pde_policylearning_b200 as P
+    from pde_policylearning_b200 import ops
+    dev = _dev()
+    torch.manual_seed(0)
+    layer = P.RNO_layer(34, 34, 12, 12, 34, return_sequences=False).to(dev)
+    B, T = 128, 3
+    x = torch.randn(B, T, 34, 32, 32, device=dev, requires_grad=True)
+    h0 = torch.randn(B, 34, 32, 32, device=dev, requires_grad=True)
+    n0 = ops.tensor_core_launches()
+    out = layer(x, h0)
+    gy = torch.randn_like(out)
+    params = list(layer.parameters())
+    got = torch.autograd.grad(out, [x, h0] + params, gy, allow_unused=True)
+    assert ops.tensor_core_launches() > n0
+    cell = layer.cell
+    h = h0
+    for t in range(T):
+        xt = x[:, t]
+        z = torch.sigmoid(cell.f1(xt) + cell.f2(h, extra_bias=cell.b1))
+        z2 = torch.sigmoid(cell.f7(xt) + cell.f8(h, extra_bias=cell.b4))
+        r = torch.sigmoid(cell.f3(xt) + cell.f4(h, extra_bias=cell.b2))
+        hh = torch.nn.functional.selu(cell.f5(xt) + cell.f6(r * h, extra_bias=cell.b3))
+        h = (1 - z) * h + z2 * hh
+    ref = torch.autograd.grad(h, [x, h0] + params, gy, allow_unused=True)
+    assert rel(out, h) < TOL, rel(out, h)
+    names = ["x", "h0"] + [n for n, _ in layer.named_parameters()]
+    worst = 0.0
+    for n, a, b in zip(names, got, ref):
+        if b is None:               # bias_h is not reached when h0 is given
+            continue
+        assert a is not None, n
+        e = rel(a, b)
+        worst = max(worst, e)
+        assert e < 5e-5, (n, e)
+    print(f"regrouped RNO layer: worst relative gradient error {worst:.2e}")
+
+
+def test_dft_forward_runs_on_tensor_cores_at_bench_shapes():
+    """Launch evidence: at the cfg2 and cfg3 plane shapes b2no_dft_forward must take the tcgen05 kernel (k_fwd_tc), not its
+    CUDA-core stages -- a silent fallback would pass every numeric test at several times the cost."""
+    from pde_policylearning_b200 import ops
+    dev = _dev()
+    for grid, half, norm, C in (((128, 128), (6, 6), "forward", 32), ((32, 32), (12, 12), "ortho", 34)):
+        plan = ops.get_plan(ops.SpecGeom(nin=grid, half=half, norm=norm), dev)
+        x = torch.randn(4, C, *grid, device=dev)
+        for which in (0, 1):
+            n0 = ops.tensor_core_launches()
+            ops.dft_forward(plan, which, x)
+            assert ops.tensor_core_launches() == n0 + 1, (grid, which)
+        spec = torch.randn(4, C, *plan.kept, dtype=torch.cfloat, device=dev)
+        w = torch.randn(C, C, device=dev)
+        n0 = ops.tensor_core_launches()
+        ops.dft_inverse(plan, 0, spec, ops.make_epilogue(pw_w=w, pw_x=x))
+        assert ops.tensor_core_launches() == n0 + 1, (grid, "inverse")
+
+
+def test_golden_pino_family_mirrors(golden):
+    """PINObserverFullField (+ PlanePredHead), PolicyModel2D, pino_models.fourier2d.FNO2d on the CUDA path
+    against the reference's fixtures a10-a12 (outputs, loss, every parameter gradient)."""
+    import pde_policylearning_b200 as P
+    dev = _dev()
+    kw = dict(modes1=[3] * 3, modes2=[3] * 3, modes3=[3] * 3, fc_dim=16, layers=[8] * 4, act="gelu", pad_ratio=0.0625)
+    w = [_run_model(P.PINObserverFullField(plane_num=3, **kw), golden("a10_pinobserver_fullfield"), dev, gtol=2e-4),
+         _run_model(P.PolicyModel2D(**kw), golden("a11_policy_model2d"), dev, gtol=2e-4),
+         _run_model(P.PinoFNO2d(modes1=[4] * 3, modes2=[3] * 3, fc_dim=12, layers=[6, 8, 8, 5], in_dim=3, out_dim=2, act="gelu",
+                                pad_ratio=[0.125, 0.0625]), golden("a12_pino_fno2d"), dev, gtol=2e-4),
+         _run_model(P.PinoFNO2d(modes1=[4] * 2, modes2=[3] * 2, fc_dim=8, layers=[4, 6, 4], in_dim=3, out_dim=1, act="gelu"),
+                    golden("a12_pino_fno2d_nopad"), dev, gtol=2e-4)]
+    print("worst relative gradient errors (full-field, policy, pino fno2d, pino fno2d no pad):", ["%.1e" % e for e in w])
+    # inference (no_grad) path of the trunk: per-sample Reynolds bias in the fused head == training path
+    c = golden("a10_pinobserver_fullfield")
+    m = P.PINObserverFullField(plane_num=3, **kw)
+    m.load_state_dict(c["state_dict"])
+    m = m.to(dev)
+    with torch.no_grad():
+        assert rel(m(*[t.to(dev) for t in c["inputs"]]), c["out"]) < TOL
+
+
+def test_pinobserver_per_sample_bias_odd_width():
+    """a trunk whose last width has no fused-head kernel (20 channels) with B > 1 and distinct Reynolds numbers --
+    eval (no_grad) output must equal the train-mode output (the Reynolds term is per sample)."""
+    import pde_policylearning_b200 as P
+    dev = _dev()
+    torch.manual_seed(2)
+    m = P.PINObserver2d(modes1=[2] * 2, modes2=[2] * 2, modes3=[2] * 2, fc_dim=12, layers=[20] * 3, act="gelu",
+                        pad_ratio=0.0625).to(dev)
+    a = torch.randn(3, 8, 8, 9, 4, device=dev)
+    re = torch.tensor([100.0, 300.0, 500.0], device=dev)
+    out_train = m(a, re)
+    with torch.no_grad():
+        out_eval = m(a, re)
+    assert rel(out_eval, out_train) < TOL
+    assert rel(out_train[0], out_train[2]) > 1e-3         # the Reynolds number does enter

@@ -83,3 +83,28 @@ def test_fno2d_and_observer_through_emulated_ops(golden):
         tgt = c["target"]
         _run_model(P.FNO2d(8, 8, 16, in_channels=3, out_channels=1), c, lambda o: P.rel_l2_loss(o, tgt, size_average=False))
         _run_model(P.FNO2dObserver(6, 6, 8), golden("a9_fno2d_observer"))
+
+
+def test_pino_family_mirrors_match_reference_fixtures(golden):
+    """PINObserver2d, PINObserverFullField (+ PlanePredHead), PolicyModel2D and pino_models.fourier2d.FNO2d: module mirrors
+    (state_dict keys, folding of fc0 / MultiplicativeNet / padding, re scaling) against the reference's fixtures."""
+    import pde_policylearning_b200 as P
+    kw = dict(modes1=[3] * 3, modes2=[3] * 3, modes3=[3] * 3, fc_dim=16, layers=[8] * 4, act="gelu", pad_ratio=0.0625)
+    with emu.installed():
+        c = golden("a10_pinobserver_fullfield")
+        _run_model(P.PINObserverFullField(plane_num=3, **kw), c)
+        c = golden("a11_policy_model2d")
+        pol = P.PolicyModel2D(**kw)
+        assert all(float(p.abs().max()) == 0.0 for p in pol.parameters())       # pinobserver.py:432-433
+        _run_model(pol, c)
+        c = golden("a12_pino_fno2d")
+        _run_model(P.PinoFNO2d(modes1=[4] * 3, modes2=[3] * 3, fc_dim=12, layers=[6, 8, 8, 5], in_dim=3, out_dim=2, act="gelu",
+                               pad_ratio=[0.125, 0.0625]), c)
+        c = golden("a12_pino_fno2d_nopad")
+        _run_model(P.PinoFNO2d(modes1=[4] * 2, modes2=[3] * 2, fc_dim=8, layers=[4, 6, 4], in_dim=3, out_dim=1, act="gelu"), c)
+        # inference path of the trunk == training path (per-sample Reynolds bias vs 1-channel map)
+        c = golden("a10_pinobserver_fullfield")
+        m = P.PINObserverFullField(plane_num=3, **kw)
+        m.load_state_dict(c["state_dict"])
+        with torch.no_grad():
+            assert rel(m(*c["inputs"]), c["out"]) < 2e-5
