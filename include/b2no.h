@@ -185,6 +185,22 @@ int b2no_rel_l2_finish(const float* sums, float* loss, float* coef, int batch, i
 int b2no_rel_l2_bwd_g(const float* x, const float* y, const float* coef, const float* g, float* dx, int batch,
                       int64_t n_per_sample, void* stream);
 
+/* ---- PINO PDE-residual loss ------------------------------------------ */
+/* Fused Channelflow_PINO_loss (libs/envs/diff_control_env.py:44-60) with FDM_NS_vorticity (:5-41) inside: one CTA per
+ * (sample, time slice) does the spectral derivatives as mode-restricted DFT contractions in shared memory, the products,
+ * the central difference in t and the warp-shuffle partial sums of both relative-L2 losses.
+ *   w (B, N, N, T) model output, t fastest; u0 (B, N, N); forcing (N, N); nu (B,) = 1 / Re; N % 4 == 0, 8 <= N <= 64.
+ *   du_p (B, T, N, N): residual planes 1 .. T-2 (plane-contiguous); fields (4, B, T, N, N): ux, wx, uy, wy for the backward;
+ *   partial (B, T, 4) scratch; loss[0] = loss_ic, loss[1] = loss_f; coef (B, 2) = the factors of the backward.
+ * bwd: dw (B, N, N, T) = gup[0] d loss_ic / dw + gup[1] d loss_f / dw (gup: 2 floats on the device). */
+int64_t b2no_pino_residual_scratch_floats(int B, int N, int T, int which);
+int b2no_pino_residual_fwd(const float* w, const float* u0, const float* forcing, const float* nu, float t_interval,
+                           float* du_p, float* fields, float* partial, float* loss, float* coef, int B, int N, int T,
+                           void* stream);
+int b2no_pino_residual_bwd(const float* w, const float* u0, const float* forcing, const float* nu, float t_interval,
+                           const float* du_p, const float* fields, const float* coef, const float* gup, float* dw,
+                           int B, int N, int T, void* stream);
+
 /* ---- optimizer ---------------------------------------------------------------- */
 /* One fused Adam update over a flat fp32 buffer (complex parameters as their (re, im) view), torch.optim.Adam
  * semantics as the reference configures it (run_pde_observers.py:134, train_pino.py:205): L2 weight decay,

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # B2NO_LIB: load another build of the same sources (A/B measurements of compile-time switches)
 LIB_PATH = os.environ.get("B2NO_LIB") or os.path.join(_HERE, "libb2no.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["plan.cu", "spectral.cu", "pointwise.cu", "tc_pointwise.cu", "tc_wgrad.cu", "tc_mlp.cu", "tc_dft.cu", "tc_mix.cu", "tc_peak.cu", "optim.cu"]
+SOURCES = ["plan.cu", "spectral.cu", "pointwise.cu", "tc_pointwise.cu", "tc_wgrad.cu", "tc_mlp.cu", "tc_dft.cu", "tc_mix.cu", "tc_peak.cu", "pino_loss.cu", "optim.cu"]
 
 MAX_DIM = 3
 NORM = {"backward": 0, "forward": 1, "ortho": 2}
@@ -128,6 +128,10 @@ def lib():
     L.b2no_gather_segments.argtypes = [vp, vp, vp, vp, i32, vp]
     f32 = C.c_float
     L.b2no_adam_step.argtypes = [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, f32, vp]
+    L.b2no_pino_residual_scratch_floats.restype = i64
+    L.b2no_pino_residual_scratch_floats.argtypes = [i32, i32, i32, i32]
+    L.b2no_pino_residual_fwd.argtypes = [vp, vp, vp, vp, f32, vp, vp, vp, vp, vp, i32, i32, i32, vp]
+    L.b2no_pino_residual_bwd.argtypes = [vp, vp, vp, vp, f32, vp, vp, vp, vp, vp, i32, i32, i32, vp]
     L.b2no_tc_peak_probe.argtypes = [i32, i32, C.POINTER(C.c_double), vp]
     for name in EXPORTS:
         getattr(L, name)
@@ -143,7 +147,7 @@ EXPORTS = [
     "b2no_act_bwd", "b2no_pw_wgrad_scratch_floats", "b2no_pw_wgrad", "b2no_mlp_head_fwd", "b2no_mlp_head_bwd_scratch_floats", "b2no_mlp_head_bwd_supported", "b2no_mlp_head_bwd",
     "b2no_rno_gate_fwd", "b2no_rno_gate_bwd", "b2no_rno_cell_bwd", "b2no_rno_reset_bwd", "b2no_rel_l2_sums", "b2no_rel_l2_bwd",
     "b2no_rel_l2_finish", "b2no_rel_l2_bwd_g", "b2no_adam_step", "b2no_gather_segments",
-    "b2no_tc_peak_probe",
+    "b2no_tc_peak_probe", "b2no_pino_residual_scratch_floats", "b2no_pino_residual_fwd", "b2no_pino_residual_bwd",
 ]
 
 

@@ -420,3 +420,37 @@ def gather_segments(flat, ptr_table, offsets, counts, nseg: int):
     check(_lib.lib().b2no_gather_segments(_ptr(flat), _ptr(ptr_table), _ptr(offsets), _ptr(counts), nseg, _stream()),
           "gather_segments")
 
+
+
+def pino_residual_supported(n: int) -> bool:
+    return 8 <= n <= 64 and n % 4 == 0
+
+
+def pino_residual_fwd(w, u0, forcing2d, nu, t_interval: float):
+    """Fused PINO residual + IC loss (csrc/pino_loss.cu).  w (B, N, N, T), u0 (B, N, N), forcing2d (N, N), nu (B,).
+    Returns (loss2 = [loss_ic, loss_f], coef (B, 2), du_p (B, T, N, N), fields (4, B, T, N, N))."""
+    _require_cuda(w, u0, forcing2d, nu)
+    B, N, _, T = w.shape
+    for t in (w, u0, forcing2d, nu):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    dev = w.device
+    du_p = torch.empty((B, T, N, N), dtype=torch.float32, device=dev)
+    fields = torch.empty((4, B, T, N, N), dtype=torch.float32, device=dev)
+    partial = torch.empty((B, T, 4), dtype=torch.float32, device=dev)
+    loss2 = torch.empty((2,), dtype=torch.float32, device=dev)
+    coef = torch.empty((B, 2), dtype=torch.float32, device=dev)
+    check(_lib.lib().b2no_pino_residual_fwd(_ptr(w), _ptr(u0), _ptr(forcing2d), _ptr(nu), float(t_interval), _ptr(du_p),
+                                            _ptr(fields), _ptr(partial), _ptr(loss2), _ptr(coef), B, N, T, _stream()),
+          "pino_residual_fwd")
+    return loss2, coef, du_p, fields
+
+
+def pino_residual_bwd(w, u0, forcing2d, nu, t_interval: float, du_p, fields, coef, gup):
+    """dw (B, N, N, T) = gup[0] d loss_ic / dw + gup[1] d loss_f / dw."""
+    B, N, _, T = w.shape
+    assert gup.dtype == torch.float32 and gup.is_contiguous() and gup.numel() == 2
+    dw = torch.empty_like(w)
+    check(_lib.lib().b2no_pino_residual_bwd(_ptr(w), _ptr(u0), _ptr(forcing2d), _ptr(nu), float(t_interval), _ptr(du_p),
+                                            _ptr(fields), _ptr(coef), _ptr(gup), _ptr(dw), B, N, T, _stream()),
+          "pino_residual_bwd")
+    return dw

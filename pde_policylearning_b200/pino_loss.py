@@ -18,8 +18,12 @@ inverse contractions run once.  Quirks kept: the signed wavenumber of index N/2 
 entry of the Laplacian is set to 1 for EVERY use, including ``-lap * w_h`` (:21-29).  Autograd differentiates the
 composition; the relative-L2 reductions use the package's loss kernels on CUDA tensors.
 
-Status: a host-level composition (GEMMs + elementwise ops), parity-tested against the oracle; the fused single-pass
-kernel (spectral derivatives + products + reduction in one launch) is SURVEY 8f rank 3."""
+Two implementations of the same sums:
+  * the FUSED kernels of csrc/pino_loss.cu (``PinoResidualLossFn``: one CTA per (sample, time slice), spectral derivatives,
+    products, central difference, warp-shuffle loss partials and the hand-derived backward; square grids 8 <= N <= 64,
+    N % 4 == 0 -- the BASELINE cfg4 grid is 64 x 64) -- what ``channelflow_pino_loss`` runs on CUDA tensors;
+  * the composition of library GEMMs with the DFT matrices below (``fdm_ns_vorticity``), kept as the differentiable
+    utility for larger grids and as the second opinion the GPU tests compare the kernels with."""
 from __future__ import annotations
 
 import math
@@ -28,6 +32,7 @@ from typing import Dict, Tuple
 import torch
 
 from . import functional as Fn
+from . import ops
 
 _tables: Dict[tuple, tuple] = {}
 
@@ -53,6 +58,13 @@ def fdm_ns_vorticity(w: torch.Tensor, v: torch.Tensor, t_interval: float = 1.0) 
     B, nx, ny, nt = w.shape
     if nx != ny or nx % 2:
         raise ValueError("the PINO residual needs a square grid of even size (diff_control_env.py:13-19)")
+    if w.is_cuda and w.dtype == torch.float32 and ops.pino_residual_supported(nx) and not (
+            torch.is_grad_enabled() and (w.requires_grad or v.requires_grad)):
+        # no gradient wanted: the fused kernel's residual planes (B, T, N, N) -> the reference's (B, N, N, T - 2)
+        wc = w.contiguous()
+        zero = torch.zeros((B, nx, ny), dtype=torch.float32, device=w.device)
+        _, _, du_p, _ = ops.pino_residual_fwd(wc, zero, zero[0].contiguous(), v.reshape(B).float().contiguous(), t_interval)
+        return du_p[:, 1:nt - 1].permute(0, 2, 3, 1)
     n, kmax, h = nx, nx // 2, nx // 2 + 1
     dt_, dev = w.dtype, w.device
     cx, sx, cy, sy = _dft_tables(n, dev, dt_)                      # cx, sx: [kx, x]; cy, sy: [ky <= N/2, y]
@@ -105,11 +117,33 @@ def _rel(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     raise RuntimeError("pde_policylearning_b200: the PINO loss reductions run only on CUDA (no CPU fallback)")
 
 
+class PinoResidualLossFn(torch.autograd.Function):
+    """[loss_ic, loss_f] = Channelflow_PINO_loss(w, u0, forcing, nu, t_interval) on the fused kernels (csrc/pino_loss.cu)."""
+
+    @staticmethod
+    def forward(ctx, w, u0, forcing2d, nu, t_interval):
+        c = lambda t: t.float().contiguous()
+        w, u0, forcing2d, nu = c(w), c(u0), c(forcing2d), c(nu)
+        loss2, coef, du_p, fields = ops.pino_residual_fwd(w, u0, forcing2d, nu, t_interval)
+        ctx.t_interval = float(t_interval)
+        ctx.save_for_backward(w, u0, forcing2d, nu, du_p, fields, coef)
+        return loss2
+
+    @staticmethod
+    def backward(ctx, g):
+        w, u0, forcing2d, nu, du_p, fields, coef = ctx.saved_tensors
+        dw = ops.pino_residual_bwd(w, u0, forcing2d, nu, ctx.t_interval, du_p, fields, coef, g.float().contiguous())
+        return dw, None, None, None, None
+
+
 def channelflow_pino_loss(model_output: torch.Tensor, u0: torch.Tensor, forcing: torch.Tensor, v: torch.Tensor,
                           t_interval: float = 1.0) -> Tuple[torch.Tensor, torch.Tensor]:
     """(loss_ic, loss_f) of diff_control_env.py:44-60: initial-condition and PDE-residual relative-L2 losses."""
     B, nx, ny, nt = model_output.shape[:4]
     out = model_output.reshape(B, nx, ny, nt)
+    if out.is_cuda and nx == ny and ops.pino_residual_supported(nx) and forcing.numel() == nx * ny:
+        loss2 = PinoResidualLossFn.apply(out, u0.reshape(B, nx, ny), forcing.reshape(nx, ny), v.reshape(B), t_interval)
+        return loss2[0], loss2[1]
     loss_ic = _rel(out[:, :, :, 0], u0)
     du = fdm_ns_vorticity(out, v, t_interval)
     f = forcing.expand(B, nx, ny, nt - 2)

@@ -232,7 +232,34 @@ def rel_l2_bwd_g(x, y, coef, g):
     return (g.to(RD) * coef.to(RD)[:, None] * (x.to(RD) - y.to(RD))).to(torch.float32)
 
 
-_NAMES = ["get_plan", "_require_cuda", "dft_forward", "make_epilogue", "dft_inverse", "pointwise", "mix", "mix_dw",
+def pino_residual_supported(n):
+    return 8 <= n <= 64 and n % 4 == 0
+
+
+def _pino_losses(w, u0, forcing2d, nu, t_interval):
+    from pde_policylearning_b200 import pino_loss
+    B, N, _, T = w.shape
+    du = pino_loss.fdm_ns_vorticity(w, nu, t_interval)                     # the GEMM composition, float64 here
+    f = forcing2d.reshape(1, N, N, 1).expand(B, N, N, T - 2)
+    rel = lambda a, b: (torch.linalg.vector_norm((a - b).reshape(B, -1), dim=1) / torch.linalg.vector_norm(b.reshape(B, -1), dim=1)).mean()
+    return torch.stack((rel(w[..., 0], u0), rel(du, f)))
+
+
+def pino_residual_fwd(w, u0, forcing2d, nu, t_interval):
+    with torch.no_grad():
+        loss2 = _pino_losses(w.to(RD), u0.to(RD), forcing2d.to(RD), nu.to(RD), t_interval).to(torch.float32)
+    return loss2, None, None, None
+
+
+def pino_residual_bwd(w, u0, forcing2d, nu, t_interval, du_p, fields, coef, gup):
+    w64 = w.to(RD).detach().requires_grad_(True)
+    with torch.enable_grad():
+        loss2 = _pino_losses(w64, u0.to(RD), forcing2d.to(RD), nu.to(RD), t_interval)
+        (dw,) = torch.autograd.grad((loss2 * gup.to(RD)).sum(), w64)
+    return dw.to(torch.float32)
+
+
+_NAMES = ["pino_residual_supported", "pino_residual_fwd", "pino_residual_bwd", "get_plan", "_require_cuda", "dft_forward", "make_epilogue", "dft_inverse", "pointwise", "mix", "mix_dw",
           "act_bwd", "pw_wgrad", "mlp_head_bwd_supported", "mlp_head_fwd", "rno_gate_fwd", "rno_gate_bwd", "rno_cell_bwd",
           "rno_reset_bwd", "rel_l2_sums", "rel_l2_finish", "rel_l2_bwd_g"]
 

@@ -835,3 +835,35 @@ def test_pinobserver_per_sample_bias_odd_width():
         out_eval = m(a, re)
     assert rel(out_eval, out_train) < TOL
     assert rel(out_train[0], out_train[2]) > 1e-3         # the Reynolds number does enter
+
+
+@pytest.mark.parametrize("N,T,B", [(64, 9, 2), (16, 5, 3), (8, 17, 2)], ids=str)
+def test_pino_residual_fused_kernels_vs_composition(N, T, B):
+    """csrc/pino_loss.cu (fused FDM_NS_vorticity + both relative-L2 losses + hand-derived backward) against the float64
+    composition of DFT-matrix products with autograd (pino_loss.fdm_ns_vorticity): Du, loss_ic, loss_f and d loss / d w."""
+    import pde_policylearning_b200 as P
+    from pde_policylearning_b200 import ops, pino_loss
+    dev = _dev()
+    torch.manual_seed(4)
+    w = torch.randn(B, N, N, T, dtype=torch.float64)
+    w = torch.fft.irfft2(torch.fft.rfft2(w, dim=(1, 2)) * torch.exp(-0.05 * torch.arange(N // 2 + 1, dtype=torch.float64) ** 2).reshape(1, 1, -1, 1),
+                         s=(N, N), dim=(1, 2))                      # smooth in y so that the residual is O(1)
+    u0 = torch.randn(B, N, N, dtype=torch.float64)
+    forcing = P.get_forcing(N).double()
+    nu = 1.0 / torch.tensor([100.0 + 150.0 * i for i in range(B)], dtype=torch.float64)
+    ti = 0.5
+    w64 = w.clone().requires_grad_(True)
+    du64 = pino_loss.fdm_ns_vorticity(w64, nu, ti)
+    relm = lambda a, b: (torch.linalg.vector_norm((a - b).reshape(B, -1), dim=1) / torch.linalg.vector_norm(b.reshape(B, -1), dim=1)).mean()
+    lic64 = relm(w64[..., 0], u0)
+    lf64 = relm(du64, forcing.expand(B, N, N, T - 2))
+    (dw64,) = torch.autograd.grad(0.7 * lic64 + 1.3 * lf64, w64)
+    wd = w.float().to(dev).requires_grad_(True)
+    lic, lf = P.channelflow_pino_loss(wd, u0.float().to(dev), forcing.float().to(dev), nu.float().to(dev), ti)
+    (dw,) = torch.autograd.grad(0.7 * lic + 1.3 * lf, wd)
+    assert abs(lic.item() - lic64.item()) <= 2e-6 * abs(lic64.item()), (lic.item(), lic64.item())
+    assert abs(lf.item() - lf64.item()) <= 1e-5 * abs(lf64.item()), (lf.item(), lf64.item())
+    assert rel(dw, dw64) < 2e-5, rel(dw, dw64)
+    with torch.no_grad():
+        du = P.fdm_ns_vorticity(wd.detach(), nu.float().to(dev), ti)
+    assert rel(du, du64) < TOL, rel(du, du64)
