@@ -111,6 +111,11 @@ int64_t b2no_plan_workspace_floats(const b2no_plan* plan, int64_t batch, int64_t
 /* 1 = use the tcgen05 tensor-core kernels where the shape is eligible (default on sm_100), 0 = CUDA-core kernels
  * only.  Returns the mode now in force.  Both paths are CUDA; neither is a CPU fallback. */
 int b2no_set_tensor_core_mode(int on);
+/* Tensor-core precision mode (north_star: "<= 1e-5 in fp32, <= 2e-2 when the reduced tensor-core mode is enabled, stated per
+ * config"): 0 = fp32-accurate, every product issued three times on tf32 splits (3xTF32; default); 1 = single-pass TF32
+ * (one kind::tf32 MMA per product, no hi/lo split work in the issue loop; measured error ~1e-3).  Activations, spectra and
+ * weights stay fp32 in HBM in both modes.  Returns the mode now in force. */
+int b2no_set_precision(int mode);
 /* number of tcgen05 kernel launches issued so far by this process (evidence for tests / bench) */
 int64_t b2no_tensor_core_launches(void);
 

@@ -3,7 +3,7 @@
 The arithmetic lives in libb2no.so (hand-written CUDA for sm_100a behind the C ABI in include/b2no.h);
 this package is the host-side mirror of the reference's operator interface.  There is no CPU fallback."""
 from . import _lib  # noqa: F401
-from .ops import SpecGeom  # noqa: F401
+from .ops import SpecGeom, set_precision  # noqa: F401
 from .functional import (spectral_block, pointwise_conv, pointwise_conv2, mlp_head, rel_l2_loss,  # noqa: F401
                          rno_gate)
 from .modules import (  # noqa: F401

@@ -102,6 +102,7 @@ def lib():
     L.b2no_plan_workspace_floats.restype = i64
     L.b2no_plan_workspace_floats.argtypes = [vp, i64, i64]
     L.b2no_set_tensor_core_mode.argtypes = [i32]
+    L.b2no_set_precision.argtypes = [i32]
     L.b2no_tensor_core_launches.restype = i64
     L.b2no_kernel_launches.restype = i64
     L.b2no_dft_forward.argtypes = [vp, i32, vp, vp, vp, i64, vp]
@@ -142,7 +143,7 @@ def lib():
 EXPORTS = [
     "b2no_version", "b2no_error_string", "b2no_device_info",
     "b2no_plan_create", "b2no_plan_destroy", "b2no_plan_kept", "b2no_plan_workspace_floats",
-    "b2no_set_tensor_core_mode", "b2no_tensor_core_launches", "b2no_kernel_launches",
+    "b2no_set_tensor_core_mode", "b2no_set_precision", "b2no_tensor_core_launches", "b2no_kernel_launches",
     "b2no_dft_forward", "b2no_dft_inverse", "b2no_mix", "b2no_mix_dw",
     "b2no_act_bwd", "b2no_pw_wgrad_scratch_floats", "b2no_pw_wgrad", "b2no_mlp_head_fwd", "b2no_mlp_head_bwd_scratch_floats", "b2no_mlp_head_bwd_supported", "b2no_mlp_head_bwd",
     "b2no_rno_gate_fwd", "b2no_rno_gate_bwd", "b2no_rno_cell_bwd", "b2no_rno_reset_bwd", "b2no_rel_l2_sums", "b2no_rel_l2_bwd",

@@ -19,10 +19,21 @@ extern long long g_b2no_launches;
     g_b2no_launches++;                             \
   } while (0)
 
+// debug / ablation switches are environment variables read ONCE per process (never on the launch path)
+#include <stdlib.h>
+static inline int b2no_env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+#define B2NO_ENV_ONCE(var, name, dflt) static const int var = b2no_env_int(name, dflt)
+
 static inline int b2no_ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 static inline int b2no_round_up(int a, int b) { return ((a + b - 1) / b) * b; }
 
 int b2no_sm_count();   // cached, current device
+// tensor-core products per fp32 product: 3 = 3xTF32 (hi*hi + lo*hi + hi*lo, fp32 parity <= 1e-5), 1 = single-pass TF32
+// (hi*hi only: the reduced-precision tensor-core mode, tolerance 2e-2 class)  -- b2no_set_precision()
+int b2no_tc_passes();
 bool b2no_tc_available();
 int b2no_tc_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* out, int batch,
                     int ci, int hidden, int co2, long pixels, int b1_per_sample, int act, cudaStream_t st);

@@ -40,6 +40,7 @@ struct FdTc {
   const float* tb; const float* mimg;
   float* spec;
   int debug;   // ablation switches (B2NO_FD_DEBUG): 1 no converter TMEM stores, 2 no MMAs, 4 no hand-over stores, 8 no lo split
+  int npass;   // 3: 3xTF32, 1: single-pass TF32 (never merged)
 };
 
 struct FdLayout { uint32_t tbh, tbl, b2, b2_bytes, xch, mts, mts_stride, stages, bars, total; };
@@ -180,7 +181,7 @@ k_fwd_tc(const __grid_constant__ CUtensorMap tmx, const FdTc p) {
 #pragma unroll
             for (int j = 0; j < 4; j++) mma_tf32_ts(d, xa + 32 + 8 * j, dt + (uint64_t)(j * 16), idesc, 1u);
           } else {
-            for (int pass = 0; pass < ((p.debug & 2) ? 0 : 3); pass++) {
+            for (int pass = 0; pass < ((p.debug & 2) ? 0 : p.npass); pass++) {
               const uint32_t ac = pass == 1 ? xa + 32 : xa;
               const uint64_t dt = (pass == 2 ? d_tl : d_th) + (uint64_t)(c * 64);     // 32 K elements = 8 chunks of 128 B
 #pragma unroll
@@ -211,7 +212,7 @@ k_fwd_tc(const __grid_constant__ CUtensorMap tmx, const FdTc p) {
             for (int j = 0; j < H / 8; j++)
               mma_tf32_ts(d, t_mt + H + 8 * j, db2 + (uint64_t)(j * (2 * kB2Lbo / 16)), idesc, 1u);
           } else {
-            for (int pass = 0; pass < 3; pass++) {
+            for (int pass = 0; pass < p.npass; pass++) {
               const uint32_t am = pass == 1 ? t_mt + H : t_mt;
               const uint32_t bb = (pass == 2 ? bl : bh) + (uint32_t)(r * H / 4) * kB2Lbo;
               const uint64_t db2 = smem_desc(bb, kB2Lbo, kB2Sbo, LAYOUT_NONE);
@@ -432,11 +433,11 @@ int b2no_tc_dft_forward(const b2no_plan* plan, int which, const float* x, float*
   const long rows = planes * tf.H;
   p.tiles = (rows + 127) / 128;
   p.tb = tf.tb; p.mimg = tf.mimg; p.spec = spec;
-  { const char* dbg = getenv("B2NO_FD_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
-  {
-    const char* mg = getenv("B2NO_FD_MERGE");
-    p.MG = (128u + 4u * p.N1 + 2u * p.H + 4u * p.R * p.N1 <= 512u && !(mg && mg[0] == '0')) ? 1 : 0;
-  }
+  B2NO_ENV_ONCE(env_debug, "B2NO_FD_DEBUG", 0);
+  B2NO_ENV_ONCE(env_merge, "B2NO_FD_MERGE", 1);
+  p.debug = env_debug;
+  p.npass = b2no_tc_passes();
+  p.MG = (128u + 4u * p.N1 + 2u * p.H + 4u * p.R * p.N1 <= 512u && env_merge != 0 && p.npass == 3) ? 1 : 0;
   if (!p.MG && 128u + 2u * p.N1 + 2u * p.H + 2u * p.R * p.N1 > 512u) return 1;
   int dev = 0, max_smem = 0;
   B2NO_CHECK_CUDA(cudaGetDevice(&dev));

@@ -36,7 +36,7 @@ namespace {
 constexpr int kMixThreads = 256;
 
 struct MixTc {
-  int B, Cq, Cp, Kt, Kp, Np, conjt, accumulate;
+  int B, Cq, Cp, Kt, Kp, Np, conjt, accumulate, npass;
   const float2* in;
   float2* out;
   b2no_weights w;
@@ -130,7 +130,7 @@ k_mix_tc(const MixTc p) {
       if (warp == 0) {
         if (elect_one()) {
           uint32_t acc = 0;
-          for (int pass = 0; pass < 3; pass++) {
+          for (int pass = 0; pass < p.npass; pass++) {
             const uint32_t a = pass == 1 ? t_al : t_ah;
             const uint64_t db = pass == 2 ? d_bl : d_bh;
             for (int ks = 0; ks < Kp / 8; ks++) {
@@ -180,7 +180,7 @@ constexpr uint32_t kDwLbo = 144;                 // bytes between K-adjacent cor
 constexpr uint32_t kDwSbo = (kDwKB / 4) * kDwLbo;  // bytes between 8-row groups
 
 struct DwTc {
-  int B, Ci, Co, Kt, Np, accumulate;
+  int B, Ci, Co, Kt, Np, accumulate, npass;
   const float2* xh;
   const float2* gyh;
   b2no_weights w;
@@ -253,7 +253,7 @@ k_dw_tc(const DwTc p) {
       __syncthreads();
       if (warp == 0) {
         if (elect_one()) {
-          for (int pass = 0; pass < 3; pass++) {
+          for (int pass = 0; pass < p.npass; pass++) {
             const uint32_t aoff = pass == 1 ? abytes : 0u;                       // A: hi, lo, hi
             const uint32_t boff = 2 * abytes + (pass == 2 ? bbytes : 0u);        // B: hi, hi, lo
             const uint64_t da = smem_desc(sbase + aoff, kDwLbo, kDwSbo, LAYOUT_NONE);
@@ -321,7 +321,7 @@ int b2no_tc_mix(const b2no_plan* p, int mode, const float* in, const b2no_weight
   memset(&q, 0, sizeof(q));
   q.B = batch; q.Cq = mode == 0 ? ci : co; q.Cp = mode == 0 ? co : ci; q.Kt = total_modes(p);
   q.Kp = b2no_round_up(2 * q.Cq, 16); q.Np = b2no_round_up(2 * q.Cp, 16);
-  q.conjt = mode; q.accumulate = accumulate;
+  q.conjt = mode; q.accumulate = accumulate; q.npass = b2no_tc_passes();
   q.in = (const float2*)in; q.out = (float2*)out; q.w = *w; q.mm = make_mode_map(p);
   if (q.Np > 256 || 2 * q.Kp + q.Np > 512) return 1;
   const size_t smem = 2 * (size_t)q.Np * q.Kp * 4 + 1024;
@@ -343,7 +343,7 @@ int b2no_tc_mix_dw(const b2no_plan* p, const float* xh, const float* gyh, const 
   DwTc q;
   memset(&q, 0, sizeof(q));
   q.B = batch; q.Ci = ci; q.Co = co; q.Kt = total_modes(p); q.Np = b2no_round_up(2 * co, 16);
-  q.accumulate = accumulate;
+  q.accumulate = accumulate; q.npass = b2no_tc_passes();
   q.xh = (const float2*)xh; q.gyh = (const float2*)gyh; q.w = *dw; q.mm = make_mode_map(p);
   if (2 * ci > 128 || q.Np > 256) return 1;
   const size_t smem = 2 * (size_t)16 * kDwSbo + 2 * (size_t)(q.Np / 8) * kDwSbo + 1024;

@@ -31,6 +31,7 @@ constexpr int kThreadsMlp = 192 + kEpiThreads;
 
 struct MlpTc {
   int B, Ci, Cip, H, Hp, NC, N2, Co2, S, fbufs, mode, act, b1_per_sample, dact, direct;
+  int npass;   // 3: 3xTF32, 1: single-pass TF32
   int tiles_per_img;
   long tiles, tiles_per_cta, P;
   const float* w1; const float* b1; const float* w2; const float* b2; const float* g; const float* dz;
@@ -168,7 +169,7 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
         const uint32_t d = t_acc1 + 64u * ab;
         const uint64_t woff = (uint64_t)((uint32_t)c * 8u * sbo1 / 16u);   // 64 rows = 8 row groups
         uint32_t acc = 0;
-        for (int pass = 0; pass < 3; pass++) {
+        for (int pass = 0; pass < p.npass; pass++) {
           const uint32_t ac = pass == 1 ? t_x + p.Cip : t_x;
           const uint64_t dw = (pass == 2 ? d_w1l : d_w1h) + woff;
           for (int k = 0; k < k1; k++) { mma_tf32_ts(d, ac + 8 * k, dw + (uint64_t)(k * 16), id1, acc); acc = 1; }
@@ -200,7 +201,7 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
           const uint32_t d = t_acc2 + (uint32_t)(it & 1) * p.N2;
           const uint32_t fa = t_f + 128u * fb;
           const uint64_t koff = (uint64_t)(c * 16 * 8);   // 64 k = 16 chunks of 4, 128 B each -> /16
-          for (int pass = 0; pass < 3; pass++) {
+          for (int pass = 0; pass < p.npass; pass++) {
             const uint32_t ac = pass == 1 ? fa + 64 : fa;
             const uint64_t dw = (pass == 2 ? d_w2l : d_w2h) + koff;
             for (int k = 0; k < 8; k++) mma_tf32_ts(d, ac + 8 * k, dw + (uint64_t)(k * 16), id2, (c > 0 || pass > 0 || k > 0) ? 1u : 0u);
@@ -506,6 +507,7 @@ int b2no_tc_mlp_fwd(const float* x, const float* w1, const float* b1, const floa
                     int ci, int hidden, int co2, long pixels, int b1_per_sample, int act, cudaStream_t st) {
   MlpTc p;
   memset(&p, 0, sizeof(p));
+  p.npass = b2no_tc_passes();
   p.B = batch; p.Ci = ci; p.H = hidden; p.Co2 = co2; p.mode = 0; p.act = act; p.b1_per_sample = b1_per_sample;
   p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.out = out;
   int grid = 0;
@@ -520,6 +522,7 @@ extern "C" int b2no_mlp_head_bwd_supported(int ci, int hidden, int64_t pixels) {
   if (pixels < 128 || pixels % 128 != 0 || ci < 1 || ci > 64 || hidden < 1 || hidden > 512) return 0;
   MlpTc p;
   memset(&p, 0, sizeof(p));
+  p.npass = b2no_tc_passes();
   p.Cip = b2no_round_up(ci, 8); p.Hp = b2no_round_up(hidden, 64); p.N2 = b2no_round_up(ci, 16); p.fbufs = 1; p.S = 2;
   if (mlp_tmem_cols(p) > 512) return 0;
   int dev = 0, max_smem = 0;
@@ -539,6 +542,7 @@ extern "C" int b2no_mlp_head_bwd(const float* x, const float* w1, const float* b
   cudaStream_t st = (cudaStream_t)stream;
   MlpTc p;
   memset(&p, 0, sizeof(p));
+  p.npass = b2no_tc_passes();
   p.B = batch; p.Ci = ci; p.H = hidden; p.Co2 = 1; p.mode = 1; p.act = act; p.b1_per_sample = b1_per_sample;
   p.w1 = w1; p.b1 = b1; p.w2 = w2; p.g = g; p.out = gx; p.gz = gz; p.dw2_partial = partial;
   p.dz = dact_z; p.dact = dact_z ? dact : 0;

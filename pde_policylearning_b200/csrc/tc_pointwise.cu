@@ -56,6 +56,7 @@ struct PwTc {
   float* preact; float* y;
   int act, dact;
   int debug;          // bit0 no stores, bit1 no MMAs
+  int npass;          // 3: 3xTF32, 1: single-pass TF32 (hi * hi only)
 };
 
 struct PwLayout {
@@ -208,7 +209,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
         const uint32_t xa = a_base + (uint32_t)a * a_width;
         uint32_t acc = 0;
         if (!nomma && elect_one()) {
-          for (int pass = 0; pass < 3; pass++) {
+          for (int pass = 0; pass < p.npass; pass++) {
             const uint32_t ac = pass == 1 ? xa + p.C1p : xa;
             const uint64_t dw = pass == 2 ? d_w1l : d_w1h;
             for (int k = 0; k < p.C1p / 8; k++) {
@@ -218,7 +219,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
           }
           if (p.C2p) {
             const uint32_t x2 = xa + 2 * p.C1p;
-            for (int pass = 0; pass < 3; pass++) {
+            for (int pass = 0; pass < p.npass; pass++) {
               const uint32_t ac = pass == 1 ? x2 + p.C2p : x2;
               const uint64_t dw = pass == 2 ? d_w2l : d_w2h;
               for (int k = 0; k < p.C2p / 8; k++) mma_tf32_ts(d, ac + 8 * k, dw + (uint64_t)(k * 16), idesc, 1);
@@ -228,7 +229,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
             // B operand A'[n = channel][k = (row, q)]: K-chunks outermost (LBO = Np/8 * 128), channel groups 128 B apart
             const uint64_t d_ah = smem_desc(st + L.ah, lbo_a, 128, LAYOUT_NONE);
             const uint64_t d_al = smem_desc(st + L.al, lbo_a, 128, LAYOUT_NONE);
-            for (int pass = 0; pass < 3; pass++) {
+            for (int pass = 0; pass < p.npass; pass++) {
               const uint32_t tcn = pass == 1 ? t_lo : t_hi;
               const uint64_t da = pass == 2 ? d_al : d_ah;
               for (int k = 0; k < p.Ks / 8; k++)
@@ -455,39 +456,49 @@ k_inv_h(const float2* __restrict__ spec, const float2* __restrict__ M, float* __
   }
   __syncthreads();
   const int ng = Np >> 3, nq = Qp >> 2;
-  const int per_row = nq * ng * 16;                    // (kq, og, o8, l0): 2 floats each
+  const int per_row = nq * ng * 8;                     // (kq, og, o8): the two ky of a q-quad (4 floats = 16 B) per thread
   const int rows = H - h0 < kInvHB ? H - h0 : kInvHB;
-  // a thread owns one (kq, og, o8, l0) output slot: its Kx spectrum values do not depend on the row, so they are
-  // read once into registers and every row costs Kx x (one broadcast LDS of M + 4 FMA)
+  // A thread owns one (kq, og, o8) slot = TWO modes ky = 2 kq, 2 kq + 1 of one channel: its 2 Kx spectrum values do not
+  // depend on the row, so they are read once into registers; every row then costs Kx x (one broadcast LDS.64 of M + four
+  // packed FFMA2) for two complex outputs, stored as one 16-byte word.  (One output per thread and scalar FMAs made this
+  // kernel issue-bound: 5 instructions per complex MAC, 60 us at the RNO shape.)
+  //   acc_a += Re M * v,  acc_b += Im M * v   ->   S = (acc_a.x - acc_b.y) + i (acc_a.y + acc_b.x)
   for (int e = threadIdx.x; e < per_row; e += 256) {
-    const int l0 = e & 1, o8 = (e >> 1) & 7;
-    const int r = e >> 4;
+    const int o8 = e & 7;
+    const int r = e >> 3;
     const int og = r % ng, kq = r / ng;
-    const int ky = kq * 2 + l0, o = og * 8 + o8;
-    const bool valid = o < Co && ky < Ky;
-    float2 v[KXM];
+    const int ky0 = kq * 2, o = og * 8 + o8;
+    const bool valid0 = o < Co && ky0 < Ky, valid1 = o < Co && ky0 + 1 < Ky;
+    float2 v0[KXM], v1[KXM];
 #pragma unroll
-    for (int kx = 0; kx < KXM; kx++)
-      v[kx] = (valid && kx < Kx) ? s_spec[o * stride + kx * Ky + ky] : make_float2(0.f, 0.f);
-    const size_t off0 = ((size_t)b * H + h0) * Qp * Np + (size_t)kq * ng * 32 + og * 32 + o8 * 4 + l0 * 2;
+    for (int kx = 0; kx < KXM; kx++) {
+      v0[kx] = (valid0 && kx < Kx) ? s_spec[o * stride + kx * Ky + ky0] : make_float2(0.f, 0.f);
+      v1[kx] = (valid1 && kx < Kx) ? s_spec[o * stride + kx * Ky + ky0 + 1] : make_float2(0.f, 0.f);
+    }
+    const size_t off0 = ((size_t)b * H + h0) * Qp * Np + (size_t)kq * ng * 32 + og * 32 + o8 * 4;
     for (int hl = 0; hl < rows; hl++) {
-      float sr = 0.f, si = 0.f;
+      float2 a0 = make_float2(0.f, 0.f), b0 = a0, a1 = a0, b1 = a0;
 #pragma unroll
       for (int kx = 0; kx < KXM; kx++) {
         if (kx < Kx) {
           const float2 m = s_m[kx * kInvHB + hl];
-          sr = fmaf(m.x, v[kx].x, fmaf(-m.y, v[kx].y, sr));
-          si = fmaf(m.x, v[kx].y, fmaf(m.y, v[kx].x, si));
+          const float2 mr = make_float2(m.x, m.x), mi = make_float2(m.y, m.y);
+          a0 = __ffma2_rn(mr, v0[kx], a0);
+          b0 = __ffma2_rn(mi, v0[kx], b0);
+          a1 = __ffma2_rn(mr, v1[kx], a1);
+          b1 = __ffma2_rn(mi, v1[kx], b1);
         }
       }
       const size_t off = off0 + (size_t)hl * Qp * Np;
-      *reinterpret_cast<float2*>(ahi + off) = make_float2(sr, si);   // fp32; k_pw_tc's converter warps make the hi / lo split
+      // fp32; k_pw_tc's converter warps make the hi / lo split
+      *reinterpret_cast<float4*>(ahi + off) = make_float4(a0.x - b0.y, a0.y + b0.x, a1.x - b1.y, a1.y + b1.x);
     }
   }
 }
 
 int g_tc_state = -1;  // -1 unknown, 0 off, 1 on
 long g_tc_launches = 0;
+int g_tc_npass = 3;
 
 }  // namespace
 
@@ -507,6 +518,12 @@ bool b2no_tc_available() {
 }
 
 extern "C" int64_t b2no_tensor_core_launches(void) { return g_tc_launches; }
+int b2no_tc_passes() { return g_tc_npass; }
+// 0 = fp32-accurate (3xTF32, default), 1 = single-pass TF32.  Returns the mode now in force.
+extern "C" int b2no_set_precision(int mode) {
+  g_tc_npass = mode == 1 ? 1 : 3;
+  return g_tc_npass == 1 ? 1 : 0;
+}
 void b2no_tc_count_launch() { g_tc_launches++; }
 
 extern "C" int b2no_set_tensor_core_mode(int on) {
@@ -623,10 +640,9 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
   long grid = p.tiles < b2no_sm_count() ? p.tiles : b2no_sm_count();
   p.tiles_per_cta = (p.tiles + grid - 1) / grid;
   grid = (p.tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
-  {
-    const char* dbg = getenv("B2NO_TC_DEBUG");
-    p.debug = dbg ? atoi(dbg) : 0;
-  }
+  B2NO_ENV_ONCE(env_debug, "B2NO_TC_DEBUG", 0);
+  p.debug = env_debug;
+  p.npass = b2no_tc_passes();
 #define LAUNCH(M)                                                                                                  \
   do {                                                                                                             \
     B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_pw_tc<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));  \

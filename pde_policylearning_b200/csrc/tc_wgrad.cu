@@ -33,6 +33,7 @@ struct WgTc {
   long tiles, tiles_per_cta;
   float* partial;
   int debug;    // ablation (B2NO_WG_DEBUG): 1 no X-lo pass, 2 no G conversion, 4 no MMAs
+  int npass;    // 3: 3xTF32, 1: single-pass TF32 (G_hi x X_hi only, accumulator columns [0, Cip))
 };
 
 struct WgLayout { uint32_t gbytes, xbytes, x, stage_bytes, dbs, bars, total; };
@@ -154,12 +155,14 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
               const uint64_t dx = smem_desc(st + L.x + (uint32_t)(sub * nbs + j) * 2 * NW * 128, 16, 1024, LAYOUT_SW128);
 #pragma unroll
               for (int ks = 0; ks < 4; ks++) {
-                mma_tf32_ts(d, a0 + (uint32_t)(j * 32 + ks * 8), dx + (uint64_t)(ks * 2), idesc2, a2);
+                mma_tf32_ts(d, a0 + (uint32_t)(j * 32 + ks * 8), dx + (uint64_t)(ks * 2), p.npass == 3 ? idesc2 : idesc, a2);
                 a2 = 1;
               }
+              if (p.npass == 3) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ks++)
-                mma_tf32_ts(d, a0 + (uint32_t)(SUB + j * 32 + ks * 8), dx + (uint64_t)(ks * 2), idesc, 1u);
+                for (int ks = 0; ks < 4; ks++)
+                  mma_tf32_ts(d, a0 + (uint32_t)(SUB + j * 32 + ks * 8), dx + (uint64_t)(ks * 2), idesc, 1u);
+              }
             }
           }
           if (sub == nsub - 1) mma_commit(&empty[s]);
@@ -286,8 +289,10 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmg, const __grid_constant__ CUte
           tmem_ld16(t_acc + lane_base + (uint32_t)(mb * 2 * NW + c0), v);
           tmem_ld16(t_acc + lane_base + (uint32_t)(mb * 2 * NW + NW + c0), u);
           tmem_ld_wait();
+          if (p.npass == 3) {
 #pragma unroll
-          for (int j = 0; j < 16; j++) v[j] += u[j];
+            for (int j = 0; j < 16; j++) v[j] += u[j];
+          }
           if (o < p.Co) {
 #pragma unroll
             for (int j = 0; j < 16; j++) {
@@ -332,7 +337,8 @@ int b2no_tc_wgrad(const float* g, const float* x, float* partial, int max_blocks
   // (155 us vs 87 us) -- the cost is per chunk hand-over (~0.7 us), not per pixel, so chunks are as large as TMEM allows;
   // a third 64-px slot (B2NO_WG_SLOTS=3) changes nothing (93.6 vs 93.4 us): the converters do not wait for free slots
   p.SUB = p.mblocks == 1 ? 64 : 32;
-  { const char* ns = getenv("B2NO_WG_SLOTS"); p.NS = (p.mblocks == 1 && ns && ns[0] == '3') ? 3 : 2; }
+  B2NO_ENV_ONCE(env_slots, "B2NO_WG_SLOTS", 2);
+  p.NS = (p.mblocks == 1 && env_slots == 3) ? 3 : 2;
   if (wg_tmem_cols(p) > 512) p.NS = 2;
   if (p.mblocks > 3 || wg_tmem_cols(p) > 512) return 1;
   // bytes in flight decide an HBM-bound kernel: take the largest tile that still leaves >= 4 stages, else the deepest ring
@@ -355,7 +361,9 @@ int b2no_tc_wgrad(const float* g, const float* x, float* partial, int max_blocks
   p.tiles_per_cta = (p.tiles + grid - 1) / grid;
   grid = (p.tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
   p.partial = partial;
-  { const char* dbg = getenv("B2NO_WG_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+  B2NO_ENV_ONCE(env_debug, "B2NO_WG_DEBUG", 0);
+  p.debug = env_debug;
+  p.npass = b2no_tc_passes();
   CUtensorMap tmg, tmx;
   {
     uint64_t dims[3] = {(uint64_t)pixels, (uint64_t)co, (uint64_t)batch};

@@ -28,6 +28,16 @@ def set_tensor_core_mode(on: bool) -> bool:
     return bool(_lib.lib().b2no_set_tensor_core_mode(1 if on else 0))
 
 
+def set_precision(mode: str) -> str:
+    """'fp32' (default): every tensor-core product is issued three times on tf32 splits (3xTF32), outputs match the
+    reference's fp32 torch.fft / einsum path to <= 1e-5.  'tf32': single-pass TF32 tensor-core mode (one MMA per product),
+    the reduced-precision mode of the north star (tolerance 2e-2; measured ~1e-3).  Data stays fp32 in HBM either way."""
+    modes = {"fp32": 0, "3xtf32": 0, "tf32": 1, "fast": 1}
+    if mode not in modes:
+        raise ValueError(f"precision mode {mode!r}: expected 'fp32' or 'tf32'")
+    return "tf32" if _lib.lib().b2no_set_precision(modes[mode]) == 1 else "fp32"
+
+
 def tensor_core_launches() -> int:
     return int(_lib.lib().b2no_tensor_core_launches())
 

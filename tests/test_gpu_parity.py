@@ -867,3 +867,32 @@ def test_pino_residual_fused_kernels_vs_composition(N, T, B):
     with torch.no_grad():
         du = P.fdm_ns_vorticity(wd.detach(), nu.float().to(dev), ti)
     assert rel(du, du64) < TOL, rel(du, du64)
+
+
+def test_single_pass_tf32_mode_within_2e2():
+    """g1: the reduced-precision tensor-core mode (one kind::tf32 MMA per product instead of the 3xTF32 triple) -- FNO2d
+    block stack, RNO conv and the projection head stay within the north star's 2e-2 of the float64 restatement, and the
+    mode really changes the arithmetic (error above the fp32-mode level)."""
+    import pde_policylearning_b200 as P
+    from oracle import restated as rs
+    dev = _dev()
+    torch.manual_seed(9)
+    obs = P.FNO2dObserver(12, 12, 32).to(dev)
+    p = torch.randn(4, 128, 128, 1, device=dev)
+    tgt = torch.randn(4, 1, 128, 128, device=dev)
+    sd = {k: (v.detach().cpu().to(torch.complex128) if v.is_complex() else v.detach().cpu().double()) for k, v in obs.state_dict().items()}
+    ref = rs.fno2d_observer_forward(sd, p.cpu().double(), 12)
+    errs = {}
+    try:
+        for mode in ("fp32", "tf32"):
+            assert P.set_precision(mode) == mode
+            out = obs(p)
+            loss = P.rel_l2_loss(out, tgt, size_average=False)
+            gs = torch.autograd.grad(loss, list(obs.parameters()))
+            assert all(torch.isfinite(g).all() for g in gs)
+            errs[mode] = rel(out, ref)
+    finally:
+        P.set_precision("fp32")
+    print("FNO2dObserver 128x128 output error vs float64:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs["tf32"] < 2e-2
+    assert errs["tf32"] > 3 * errs["fp32"]
