@@ -670,5 +670,24 @@ extern "C" int b2no_dft_inverse(const b2no_plan* p, int which, const float* spec
   const float2* T1 = which == 0 ? p->m_inv[1] : p->m_adjfwd[1];
   rc = run_cmat(Bb, A, T1, bc * n[0], p->K[1], n[1], Kl, st);
   if (rc) return rc;
+  // 3-D (PINO, basics.py:114-143 + pinobserver.py:222-226): the last transform stage is 2 K_last FMAs per output, the 1x1
+  // convolution next to it Ci of them -- the convolution (+ bias, activation, saved pre-activation) goes to the tensor-core
+  // tile kernel as a pure pointwise op, with the transform's result T entering through `add`:
+  //     T = irfft_last(stage) (CUDA cores, no epilogue)      y = epilogue(W x + bias + T) (tcgen05, k_pw_tc)
+  // (the tile kernel's own last-stage operand needs pixel tiles that are whole rows; 73-point rows are not)
+  if (epi && e.pw_ci > 0 && !e.add && b2no_tc_available() && P % 128 == 0) {
+    float* T = (float*)(Bb + (size_t)bc * n[0] * p->K[1] * Kl);
+    EpiDev e0;
+    memset(&e0, 0, sizeof(e0));
+    rc = run_c2r(A, T, tab, e0, batch, channels, (long)n[0] * n[1], n[2], P, Kl, npad, st);
+    if (rc) return rc;
+    b2no_epilogue epi2 = *epi;
+    epi2.add = T;
+    rc = b2no_tc_pointwise(nullptr, which, nullptr, y, nullptr, batch, channels, P, &epi2, st);
+    if (rc != 1) return rc;
+    EpiDev e2 = e;
+    e2.add = T;
+    return run_c2r(nullptr, y, nullptr, e2, batch, channels, (P + 127) / 128, 128, P, 0, 128, st);
+  }
   return run_c2r(A, y, tab, e, batch, channels, (long)n[0] * n[1], n[2], P, Kl, npad, st);
 }

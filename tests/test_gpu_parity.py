@@ -896,3 +896,39 @@ def test_single_pass_tf32_mode_within_2e2():
     print("FNO2dObserver 128x128 output error vs float64:", {k: f"{v:.2e}" for k, v in errs.items()})
     assert errs["tf32"] < 2e-2
     assert errs["tf32"] > 3 * errs["fp32"]
+
+
+def test_3d_layer_pointwise_on_tensor_cores():
+    """PINO layer shape class (3-D, rows that are not multiples of the pixel tile): spectral conv + Conv1d(k=1) + bias +
+    GELU with the 1x1 convolution on the tcgen05 tile kernel (transform result handed over through `add`), y, dx and
+    parameter gradients vs the float64 closed form; the tile kernel must actually run."""
+    import pde_policylearning_b200 as P
+    from oracle import closed_form as cf
+    from pde_policylearning_b200 import ops
+    dev = _dev()
+    torch.manual_seed(6)
+    B, C, grid, m = 2, 16, (8, 8, 18), (3, 3, 4)          # 8 * 8 * 18 = 1152 = 9 * 128 pixels, rows of 18
+    conv = P.PinoSpectralConv3d(C, C, *m)
+    w = torch.randn(C, C, 1) * 0.3
+    bias = torch.randn(C)
+    x = torch.randn(B, C, *grid)
+    gy = torch.randn(B, C, *grid)
+    g64 = cf.geom_pino3d(grid, *m)
+    corners = [c.detach().clone() for c in conv.corners()]
+    x64 = x.double().requires_grad_(True)
+    w64, b64 = w.double().requires_grad_(True), bias.double().requires_grad_(True)
+    sf, si = g64.scales()
+    W = cf.gather_weight(g64, corners)
+    z64 = cf.idft_trunc(g64, torch.einsum("bi...,io...->bo...", cf.dft_trunc(g64, x64, sf), W), si) \
+        + torch.einsum("oi,bi...->bo...", w64[:, :, 0], x64) + b64.reshape(1, -1, 1, 1, 1)
+    y64 = torch.nn.functional.gelu(z64)
+    dx64, dw64, db64 = torch.autograd.grad(y64, [x64, w64, b64], gy.double())
+    conv = conv.to(dev)
+    xd = x.to(dev).requires_grad_(True)
+    wd, bd = w.to(dev).requires_grad_(True), bias.to(dev).requires_grad_(True)
+    n0 = ops.tensor_core_launches()
+    y = conv.forward_fused(xd, bias=bd, pw_weight=wd, act="gelu")
+    assert ops.tensor_core_launches() > n0, "the 3-D layer's 1x1 conv did not reach the tile kernel"
+    dx, dw, db = torch.autograd.grad(y, [xd, wd, bd], gy.to(dev))
+    errs = dict(y=rel(y, y64), dx=rel(dx, dx64), dw=rel(dw, dw64), db=rel(db, db64))
+    assert max(errs.values()) < TOL, errs
