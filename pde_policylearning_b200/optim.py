@@ -24,8 +24,13 @@ class FusedAdam:
     ``self.bucket.flat`` (so ``state_dict()`` / checkpoints of the MODEL are unchanged)."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
-                 bucket: Optional[GradBucket] = None):
+                 bucket: Optional[GradBucket] = None, overlap_allreduce: bool = False, bucket_bytes: int = 32 << 20,
+                 group=None):
+        """overlap_allreduce: sum the gradients over the ranks bucket by bucket DURING the backward (parallel.OverlappedGradSync)
+        instead of with one all-reduce after it."""
         self.bucket = bucket if bucket is not None else GradBucket(params)
+        self._overlap_cfg = (bool(overlap_allreduce), int(bucket_bytes), group)
+        self.overlap = None
         ps = self.bucket.params
         if not ps:
             raise ValueError("FusedAdam got no trainable parameters")
@@ -45,6 +50,9 @@ class FusedAdam:
         self.exp_avg = torch.zeros_like(self.flat_param)
         self.exp_avg_sq = torch.zeros_like(self.flat_param)
         self.step_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        if self._overlap_cfg[0]:
+            from .parallel import OverlappedGradSync
+            self.overlap = OverlappedGradSync(self.bucket, self._overlap_cfg[1], self._overlap_cfg[2])
 
     def zero_grad(self, set_to_none: bool = False):
         """set_to_none: drop the gradients, so that the next backward assigns them and `sync_grads()` collects
@@ -59,6 +67,9 @@ class FusedAdam:
     def sync_grads(self, group=None):
         """After backward: gather the per-parameter gradients into the flat bucket and (world > 1) sum them over the
         ranks with ONE all-reduce; `step(grad_scale=1/world)` turns the sum into the data-parallel mean."""
+        if self.overlap is not None:
+            self.overlap.finish()          # the per-bucket all-reduces were launched from the backward's gradient hooks
+            return
         self.bucket.gather()
         if dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.SUM, group=group)

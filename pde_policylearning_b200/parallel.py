@@ -153,6 +153,137 @@ class GradBucket:
         return self.flat
 
 
+class OverlappedGradSync:
+    """Gradient all-reduce launched DURING the backward, bucket by bucket ("bucket per layer, launch when that
+    layer's dW is complete, overlap with the remaining backward").
+
+    The parameters are split, from the LAST one backwards (the order in which the backward finishes them), into groups
+    of about `bucket_bytes`; every group is one contiguous range of the flat bucket.  A post-accumulate hook on every
+    parameter counts arrivals; when a group is complete its gradients are gathered into the flat range (one kernel) and
+    the range is summed over the ranks with ONE NCCL all-reduce issued on a side stream, so the collective of the late
+    layers runs underneath the backward of the early ones.  `finish()` (called by FusedAdam.sync_grads) launches what is
+    left, makes the compute stream wait for the side stream, and points every p.grad at its bucket view.  Works inside a
+    CUDA-graph capture (the side stream is forked from and joined to the capturing stream).  Semantics are those of
+    libs/pino_utils/distributed.py:23-34 (sum, then divide by the world size -- the division is folded into Adam)."""
+
+    def __init__(self, bucket: GradBucket, bucket_bytes: int = 32 << 20, group=None):
+        self.bucket, self.group = bucket, group
+        ps = bucket.params
+        if bucket.flat is None:
+            bucket.attach()
+        n = len(ps)
+        ends = [bucket.offsets[i + 1] if i + 1 < n else bucket.numel for i in range(n)]
+        self.ranges = []                       # (lo, hi): parameters lo .. hi-1, in launch order (last parameters first)
+        hi, acc = n, 0
+        for i in range(n - 1, -1, -1):
+            acc += (ends[i] - bucket.offsets[i]) * 4
+            if acc >= bucket_bytes or i == 0:
+                self.ranges.append((i, hi))
+                hi, acc = i, 0
+        self.group_of = [0] * n
+        for g, (lo, hi) in enumerate(self.ranges):
+            for i in range(lo, hi):
+                self.group_of[i] = g
+        self.flat_range = [(bucket.offsets[lo], ends[hi - 1]) for lo, hi in self.ranges]
+        self._reset()
+        self.enabled = True
+        self.comm_stream = torch.cuda.Stream(device=ps[0].device) if ps[0].is_cuda else None
+        self._host_tables = None
+        self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(ps)]
+        self.launched_during_backward = 0      # evidence for tests / bench: groups whose all-reduce started before finish()
+
+    def _reset(self):
+        self._pending = [hi - lo for lo, hi in self.ranges]
+        self._launched = [False] * len(self.ranges)
+
+    def _make_hook(self, i):
+        def hook(p):
+            if not self.enabled:
+                return
+            g = self.group_of[i]
+            self._pending[g] -= 1
+            if self._pending[g] == 0 and not self._launched[g]:
+                self._launch(g)
+                self.launched_during_backward += 1
+        return hook
+
+    def _world(self):
+        return dist.get_world_size(self.group) if dist.is_initialized() else 1
+
+    def _gather_group(self, g):
+        b = self.bucket
+        lo, hi = self.ranges[g]
+        views = b._views()
+        if b.flat.is_cuda:
+            from . import ops
+            if getattr(b, "_seg_dev", None) is None:
+                dev = b.flat.device
+                offs = list(b.offsets) + [b.numel]
+                cnts = [(2 if p.is_complex() else 1) * p.numel() for p in b.params]
+                b._seg_dev = (torch.tensor(offs, dtype=torch.int64, device=dev), torch.tensor(cnts, dtype=torch.int64, device=dev))
+                b._ptr_dev = torch.zeros(len(b.params), dtype=torch.int64, device=dev)
+                b._ptr_host = [torch.zeros(len(b.params), dtype=torch.int64).pin_memory() for _ in range(2)]
+                b._keep = []
+            capturing = torch.cuda.is_current_stream_capturing()
+            host = b._ptr_host[1 if capturing else 0]
+            keep = []
+            for i in range(lo, hi):
+                gr = b.params[i].grad
+                if gr is not None and not gr.is_contiguous():
+                    gr = gr.contiguous()
+                keep.append(gr)
+                host[i] = 0 if gr is None else gr.data_ptr()
+            (b._keep if capturing else self._keep_eager).extend(keep)
+            b._ptr_dev[lo:hi].copy_(host[lo:hi], non_blocking=True)
+            # offsets are absolute positions in the flat bucket, so the sub-tables address the same destination
+            ops.gather_segments(b.flat, b._ptr_dev[lo:hi], b._seg_dev[0][lo:hi + 1], b._seg_dev[1][lo:hi], hi - lo)
+        else:
+            for i in range(lo, hi):
+                gr = b.params[i].grad
+                if gr is None:
+                    views[i].zero_()
+                elif gr.data_ptr() != views[i].data_ptr():
+                    views[i].copy_(gr)
+
+    def _launch(self, g):
+        self._gather_group(g)
+        self._launched[g] = True
+        if self._world() > 1:
+            fs, fe = self.flat_range[g]
+            chunk = self.bucket.flat[fs:fe]
+            if self.comm_stream is not None:
+                cur = torch.cuda.current_stream(self.bucket.flat.device)
+                self.comm_stream.wait_stream(cur)
+                with torch.cuda.stream(self.comm_stream):
+                    dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+            else:
+                dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+
+    _keep_eager: List = []
+
+    def finish(self):
+        """Launch the groups the backward did not complete (parameters without a gradient count as zeros), join the side
+        stream, re-point p.grad at the bucket views."""
+        self._keep_eager = self._keep_eager[-4 * len(self.bucket.params):]
+        for g in range(len(self.ranges)):
+            if not self._launched[g]:
+                self._launch(g)
+        if self.comm_stream is not None and self._world() > 1:
+            torch.cuda.current_stream(self.bucket.flat.device).wait_stream(self.comm_stream)
+        was = self.enabled
+        self.enabled = False
+        for p, v in zip(self.bucket.params, self.bucket._views()):
+            p.grad = v
+        self.enabled = was
+        self._reset()
+        return self.bucket.flat
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
 def all_reduce_mean_scalar(t: torch.Tensor, group=None) -> torch.Tensor:
     """libs/pino_utils/distributed.py:23-34."""
     if dist.is_initialized() and dist.get_world_size(group) > 1:
