@@ -321,25 +321,31 @@ class MlpHeadFn(torch.autograd.Function):
                 dw2.reshape(ctx.shapes[2]) if need_w2 else None, db2, None)
 
 
+def mlp_head_fused_available(x, w1, w2, b1, needs_grad: bool) -> bool:
+    """True when mlp_head() runs the fused tensor-core head for these operands (the hidden tensor is never materialised)."""
+    if not x.is_cuda or w2.reshape(-1, w1.shape[0]).shape[0] != 1 or (b1 is not None and b1.dim() > 2):
+        return False
+    if needs_grad:
+        return bool(ops.mlp_head_bwd_supported(x.shape[1], w1.shape[0], math.prod(x.shape[2:]))) and x.data_ptr() % 16 == 0
+    return x.shape[1] in (8, 16, 32, 64)
+
+
 def mlp_head(x, w1, b1, w2, b2, act="gelu"):
     """Projection head Ci -> hidden -> act -> 1 (tfno.py:34-38).  The fused kernels never materialise the hidden
     tensor in the forward; shapes without a fused kernel compose two pointwise convs (hidden saved for backward)."""
     ops._require_cuda(x, w1, b1, w2, b2)
     needs_grad = torch.is_grad_enabled() and any(
         t is not None and t.requires_grad for t in (x, w1, b1, w2, b2))
-    if (needs_grad and x.is_cuda and w2.reshape(-1, w1.shape[0]).shape[0] == 1 and (b1 is None or b1.dim() <= 2)
-            and ops.mlp_head_bwd_supported(x.shape[1], w1.shape[0], math.prod(x.shape[2:]))
-            and x.data_ptr() % 16 == 0):
-        return MlpHeadFn.apply(x, w1, b1, w2, b2, act)
-    if (not needs_grad and w2.reshape(-1, w1.shape[0]).shape[0] == 1 and x.shape[1] in (8, 16, 32, 64)
-            and (b1 is None or b1.dim() <= 2)):
+    if mlp_head_fused_available(x, w1, w2, b1, needs_grad):
+        if needs_grad:
+            return MlpHeadFn.apply(x, w1, b1, w2, b2, act)
         return ops.mlp_head_fwd(_contig(x.float()), _contig(w1.reshape(w1.shape[0], -1).float()),
                                 None if b1 is None else _contig(b1.float()), _contig(w2.reshape(-1).float()),
                                 None if b2 is None else _contig(b2.float()), act)
     if b1 is not None and b1.dim() == 2:
         # the composed path's epilogue reads bias[o] only: a (batch, hidden) bias would silently use sample 0's row
-        raise ValueError("mlp_head: a per-sample bias needs the fused head kernel (in_channels in {8, 16, 32, 64}, one output "
-                         "channel); pass the per-sample term as a 1-channel map through pointwise_conv2 instead")
+        raise ValueError("mlp_head: a per-sample bias needs the fused head kernel (mlp_head_fused_available); pass the "
+                         "per-sample term as a 1-channel map through pointwise_conv2 instead")
     h = pointwise_conv(x, w1, b1, act)
     return pointwise_conv(h, w2, b2, None)
 

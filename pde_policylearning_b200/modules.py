@@ -838,9 +838,12 @@ def _pino_trunk_forward(x, re, fc0, mnet1, sp_convs, ws, mnet2, fc1, fc2, act_na
     wre = fc1.weight @ mnet2.A                                    # (fc_dim, 1)
     b1 = fc1.weight @ mnet2.bias + fc1.bias                       # (fc_dim,)
     szp = sz + num_pad[0] + num_pad[1]
-    no_grad = not (torch.is_grad_enabled() and (h.requires_grad or w1.requires_grad))
-    if no_grad and fc2.out_features == 1 and h.shape[1] in (8, 16, 32, 64):
-        # inference: fused head, per-sample bias carries the Reynolds term; hidden never materialised
+    needs_grad = torch.is_grad_enabled() and (h.requires_grad or w1.requires_grad)
+    h = h if h.is_contiguous() else h.contiguous()
+    if fc2.out_features == 1 and Fn.mlp_head_fused_available(h, w1, fc2.weight, None, needs_grad):
+        # fused head (training and inference): the per-sample bias carries the Reynolds term, the fc_dim-wide hidden
+        # tensor is never materialised in the forward; autograd reaches A / B / bias of MultiplicativeNet2 and fc1
+        # through the folded w1 / per-sample b1
         out = Fn.mlp_head(h, w1, b1[None, :] + re @ wre.t(), fc2.weight, fc2.bias, act_name)
     else:
         re_map = re.reshape(B, 1, 1, 1, 1).expand(B, 1, sx, sy, szp).contiguous()

@@ -932,3 +932,33 @@ def test_3d_layer_pointwise_on_tensor_cores():
     dx, dw, db = torch.autograd.grad(y, [xd, wd, bd], gy.to(dev))
     errs = dict(y=rel(y, y64), dx=rel(dx, dx64), dw=rel(dw, dw64), db=rel(db, db64))
     assert max(errs.values()) < TOL, errs
+
+
+def test_pinobserver_training_through_fused_head():
+    """The PINO tail in training: fused head (per-sample Reynolds bias, hidden never materialised) vs the composition of
+    two pointwise convs with the Reynolds term as a 1-channel map -- output and every parameter gradient."""
+    import pde_policylearning_b200 as P
+    from pde_policylearning_b200 import functional as Fn, ops
+    dev = _dev()
+    torch.manual_seed(8)
+    m = P.PINObserver2d(modes1=[3] * 2, modes2=[3] * 2, modes3=[3] * 2, fc_dim=32, layers=[16] * 3, act="gelu",
+                        pad_ratio=0.0625).to(dev)
+    a = torch.randn(3, 8, 8, 14, 4, device=dev)             # 14 + 1 + 1 padded time steps: 8 * 8 * 16 = 1024 pixels
+    re = torch.tensor([120.0, 260.0, 480.0], device=dev)
+    gy = torch.randn(3, 8, 8, 14, 1, device=dev)
+    params = list(m.parameters())
+    n0 = ops.tensor_core_launches()
+    assert Fn.mlp_head_fused_available(torch.empty(3, 16, 8, 8, 16, device=dev), m.fc1.weight, m.fc2.weight, None, True)
+    out = m(a, re)
+    g1 = torch.autograd.grad(out, params, gy)
+    assert ops.tensor_core_launches() > n0
+    saved = Fn.mlp_head_fused_available
+    Fn.mlp_head_fused_available = lambda *args, **kw: False
+    try:
+        out2 = m(a, re)
+        g2 = torch.autograd.grad(out2, params, gy)
+    finally:
+        Fn.mlp_head_fused_available = saved
+    assert rel(out, out2) < TOL
+    worst = max(rel(x, y) for x, y in zip(g1, g2))
+    assert worst < 5e-5, worst
