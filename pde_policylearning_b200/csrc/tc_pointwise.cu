@@ -44,6 +44,7 @@ constexpr int kThreads = 192 + kEpiThreadsPw;
 
 struct PwTc {
   int B, Co, Np, C1, C1p, C2, C2p, Ks, Qp, R, S;
+  int NA;             // TMEM A-operand buffers: 2 (conversion of tile i+1 overlaps the MMAs of tile i), or 1 when two do not fit
   int Cz;             // > 0: MODE 3 streams the saved pre-activations dz through the TMA ring, [Cz x 128 px] per stage
   int tiles_per_img;
   long tiles, tiles_per_cta, P;
@@ -84,7 +85,7 @@ __host__ __device__ inline PwLayout pw_layout(const PwTc& p) {
 }
 
 __host__ __device__ inline uint32_t pw_tmem_cols(const PwTc& p) {
-  return 2u * p.Np + 2u * p.Ks + 4u * (p.C1p + p.C2p);
+  return 2u * p.Np + 2u * p.Ks + 2u * (uint32_t)p.NA * (p.C1p + p.C2p);
 }
 
 // MODE 1: no activation;  2: GELU;  3: multiply by GELU'(dz);  0: generic (runtime act / dact, add, mul)
@@ -200,13 +201,15 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
         const uint32_t ph = (uint32_t)(it / p.S) & 1u;
         const int a = it & 1;
         const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+        const int xi = p.NA == 2 ? a : 0;                                  // A-operand buffer and its phase
+        const uint32_t xph = p.NA == 2 ? aph : ((uint32_t)it & 1u);
         mbar_wait(&full[s], ph);         // A' rows landed (and X, consumed by the converter)
-        mbar_wait(&a_full[a], aph);      // converter filled TMEM A buffer a
+        mbar_wait(&a_full[xi], xph);     // converter filled TMEM A buffer xi
         mbar_wait(&acc_empty[a], aph ^ 1u);
         tc_fence_after();
         const uint32_t st = sbase + L.stages + (uint32_t)s * L.stage_bytes;
         const uint32_t d = tbase + (uint32_t)a * p.Np;
-        const uint32_t xa = a_base + (uint32_t)a * a_width;
+        const uint32_t xa = a_base + (uint32_t)xi * a_width;
         uint32_t acc = 0;
         if (!nomma && elect_one()) {
           for (int pass = 0; pass < p.npass; pass++) {
@@ -239,7 +242,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
         }
         if (elect_one()) {
           mma_commit(&empty[s]);
-          mma_commit(&a_empty[a]);
+          mma_commit(&a_empty[xi]);
           mma_commit(&acc_full[a]);
         }
         __syncwarp();
@@ -265,8 +268,8 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
     for (long tile = t_first; tile < t_end; tile++, it++) {
       const int s = it % p.S;
       const uint32_t ph = (uint32_t)(it / p.S) & 1u;
-      const int a = it & 1;
-      const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+      const int a = p.NA == 2 ? (it & 1) : 0;
+      const uint32_t aph = p.NA == 2 ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
       mbar_wait(&full[s], ph);
       if (p.Ks) {
         // A' rows arrive as ONE fp32 image (half the bytes k_inv_h writes and this kernel reads); split it in place into
@@ -566,6 +569,8 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
     p.ahi = work;
     p.alo = work + afl;
   }
+  p.NA = 2;
+  if (pw_tmem_cols(p) > 512) p.NA = 1;          // wide operands: one A buffer (the converter then waits for the tile's MMAs)
   if (pw_tmem_cols(p) > 512) return 1;
   const bool extras = p.add || p.mul || p.gate_z;
   int mode = 0;

@@ -962,3 +962,28 @@ def test_pinobserver_training_through_fused_head():
     assert rel(out, out2) < TOL
     worst = max(rel(x, y) for x, y in zip(g1, g2))
     assert worst < 5e-5, worst
+
+
+@pytest.mark.parametrize("ci,ci2,co", [(64, 1, 128), (128, 0, 64), (72, 0, 34)], ids=str)
+def test_tile_kernel_single_a_buffer(ci, ci2, co):
+    """Wide 1x1 convolutions whose double-buffered TMEM operand does not fit 512 columns (PINO tail 64 -> 128 with the
+    Reynolds map, its dx 128 -> 64, the RNO gate dx 68 -> 34) run the tile kernel with ONE operand buffer instead of
+    dropping to the CUDA-core kernel."""
+    from pde_policylearning_b200 import ops
+    dev = _dev()
+    torch.manual_seed(12)
+    B, grid = 2, (16, 32)
+    x = torch.randn(B, ci, *grid)
+    w = torch.randn(co, ci) * 0.2
+    bias = torch.randn(co)
+    z64 = torch.einsum("oi,bi...->bo...", w.double(), x.double()) + bias.double().reshape(1, -1, 1, 1)
+    kw = {}
+    if ci2:
+        x2 = torch.randn(B, ci2, *grid)
+        w2 = torch.randn(co, ci2)
+        z64 = z64 + torch.einsum("oi,bi...->bo...", w2.double(), x2.double())
+        kw = dict(pw2_w=w2.to(dev), pw2_x=x2.to(dev))
+    n0 = ops.tensor_core_launches()
+    y = ops.pointwise(B, co, grid, dev, ops.make_epilogue(bias=bias.to(dev), pw_w=w.to(dev), pw_x=x.to(dev), act="gelu", **kw))
+    assert ops.tensor_core_launches() == n0 + 1, "tile kernel did not run"
+    assert rel(y, torch.nn.functional.gelu(z64)) < TOL
