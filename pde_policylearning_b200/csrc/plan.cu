@@ -97,10 +97,11 @@ void choose_chunks(int q2, int* qc, int* nchunk) {
   if (q2 <= 4) { *qc = 4; *nchunk = 1; return; }
   if (q2 <= 8) { *qc = 8; *nchunk = 1; return; }
   if (q2 <= 12) { *qc = 12; *nchunk = 1; return; }
-  if (q2 <= 16) { *qc = 16; *nchunk = 1; return; }
-  int n12 = (q2 + 11) / 12, n16 = (q2 + 15) / 16;
-  if (n12 * 12 < n16 * 16) { *qc = 12; *nchunk = n12; }
-  else { *qc = 16; *nchunk = n16; }
+  // chunks of 8 or 12 table rows: k_r2c_last keeps 8 * QC accumulators per thread, and the QC = 16 instantiation
+  // spilled all 128 of them to local memory (ptxas: 512 B stack) -- 1.2 ms for the 306 MB last-dim pass of the PINO layer
+  int n8 = (q2 + 7) / 8, n12 = (q2 + 11) / 12;
+  if (n12 * 12 <= n8 * 8) { *qc = 12; *nchunk = n12; }
+  else { *qc = 8; *nchunk = n8; }
 }
 
 }  // namespace
