@@ -46,7 +46,7 @@ struct MixTc {
 // ---------------------------------------------------------------------------------------------------------------------
 // k_mix_tc
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kMixThreads, 1)
+__global__ void __launch_bounds__(kMixThreads, 2)
 k_mix_tc(const MixTc p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -78,10 +78,19 @@ k_mix_tc(const MixTc p) {
   const uint64_t d_bl = smem_desc(sbase + wbytes, 128, (uint32_t)(Kp / 4) * 128, LAYOUT_NONE);
   const int ntiles = (p.B + 127) / 128;
   uint32_t phase = 0;
+  // work items = (mode, 128-sample tile), mode-major; every CTA owns a contiguous run, so a mode's weight block is staged
+  // once per CTA that touches it.  (One CTA per mode left a single CTA per SM with every gather latency exposed.)
+  const long items = (long)p.Kt * ntiles;
+  const long per_cta = (items + gridDim.x - 1) / gridDim.x;
+  const long it0 = (long)blockIdx.x * per_cta;
+  const long it1 = it0 + per_cta < items ? it0 + per_cta : items;
+  int staged = -1;
 
-  for (int k = blockIdx.x; k < p.Kt; k += gridDim.x) {
-    // ---- the mode's weight block -> shared memory (hi / lo), real-block form ----
-    {
+  for (long item = it0; item < it1; item++) {
+    const int k = (int)(item / ntiles), tile = (int)(item - (long)k * ntiles);
+    if (k != staged) {
+      // ---- the mode's weight block -> shared memory (hi / lo), real-block form ----
+      staged = k;
       int corner;
       long woff;
       decode_mode(p.mm, p.w, k, &corner, &woff);
@@ -103,29 +112,39 @@ k_mix_tc(const MixTc p) {
       }
       fence_proxy_async();
     }
-    for (int tile = 0; tile < ntiles; tile++) {
+    {
       const int b = tile * 128 + row;
       // ---- A operand: this lane's sample, all contraction channels of mode k -> TMEM (hi | lo); the two warps of a
-      //      quadrant take alternate 8-channel chunks ----
+      //      quadrant take alternate 8-channel chunks; up to three chunks (24 gathers) are in flight per thread ----
       {
         const float2* src = p.in + ((size_t)(b < p.B ? b : 0) * p.Cq) * p.Kt + k;
-        for (int c0 = grp * 8; c0 * 2 < Kp; c0 += 16) {
-          float hi[16], lo[16];
+        for (int cb = grp * 8; cb * 2 < Kp; cb += 48) {
+          float2 v[3][8];
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            float2 v = make_float2(0.f, 0.f);
-            if (b < p.B && c0 + j < p.Cq) v = __ldg(src + (size_t)(c0 + j) * p.Kt);
-            hi[2 * j] = v.x; hi[2 * j + 1] = v.y;
+          for (int u = 0; u < 3; u++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const int c = cb + 16 * u + j;
+              v[u][j] = (b < p.B && c < p.Cq) ? __ldg(src + (size_t)c * p.Kt) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+          for (int u = 0; u < 3; u++) {
+            const int c0 = cb + 16 * u;
+            if (c0 * 2 < Kp) {
+              float hi[16], lo[16];
+#pragma unroll
+              for (int j = 0; j < 8; j++) { hi[2 * j] = v[u][j].x; hi[2 * j + 1] = v[u][j].y; }
+#pragma unroll
+              for (int j = 0; j < 16; j++) lo[j] = tf32_lo(hi[j]);
+              tmem_st16(t_ah + lane_base + (uint32_t)(2 * c0), hi);
+              tmem_st16(t_al + lane_base + (uint32_t)(2 * c0), lo);
+            }
           }
-#pragma unroll
-          for (int j = 0; j < 16; j++) lo[j] = tf32_lo(hi[j]);
-          tmem_st16(t_ah + lane_base + (uint32_t)(2 * c0), hi);
-          tmem_st16(t_al + lane_base + (uint32_t)(2 * c0), lo);
         }
         tmem_st_wait();
       }
       tc_fence_before();
-      __syncthreads();       // A complete; the previous tile's epilogue has drained the accumulator
+      __syncthreads();       // A complete (and the weight block, when it was restaged); the previous item's epilogue is done
       tc_fence_after();
       if (warp == 0) {
         if (elect_one()) {
@@ -164,8 +183,9 @@ k_mix_tc(const MixTc p) {
         }
       }
       tc_fence_before();
+      __syncthreads();       // the item's MMAs are complete (bar) and every thread is past its accumulator reads: the weight
+                             // block and the A columns may be rewritten
     }
-    __syncthreads();         // every MMA of this mode has completed (bar) and every thread is past its reads
   }
   tc_fence_before();
   __syncthreads();
@@ -180,7 +200,7 @@ constexpr uint32_t kDwLbo = 144;                 // bytes between K-adjacent cor
 constexpr uint32_t kDwSbo = (kDwKB / 4) * kDwLbo;  // bytes between 8-row groups
 
 struct DwTc {
-  int B, Ci, Co, Kt, Np, accumulate, npass;
+  int B, Ci, Co, Kt, Np, Ga, accumulate, npass;      // Ga = 8-row groups of the A image that are materialised (2 Ci rows)
   const float2* xh;
   const float2* gyh;
   b2no_weights w;
@@ -191,7 +211,7 @@ __device__ __forceinline__ uint32_t dw_off(int r, int bb) {
   return (uint32_t)(r >> 3) * kDwSbo + (uint32_t)(bb >> 2) * kDwLbo + (uint32_t)(r & 7) * 16 + (uint32_t)(bb & 3) * 4;
 }
 
-__global__ void __launch_bounds__(kMixThreads, 1)
+__global__ void __launch_bounds__(kMixThreads, 2)
 k_dw_tc(const DwTc p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -199,7 +219,9 @@ k_dw_tc(const DwTc p) {
   __shared__ uint32_t tslot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Np = p.Np;
-  const uint32_t abytes = 16u * kDwSbo;                    // A image: 128 rows (i, re|im), rows >= 2Ci stay zero
+  // A image: 2 Ci rows (i, re|im) rounded up to 8; an M = 128 MMA reads 16 row groups from its base -- the groups beyond Ga
+  // are whatever follows in shared memory (the lo image, the B images) and only feed accumulator rows nobody reads
+  const uint32_t abytes = (uint32_t)p.Ga * kDwSbo;
   const uint32_t bbytes = (uint32_t)(Np / 8) * kDwSbo;     // B image: Np rows (o, re|im)
   uint8_t* s_ah = smem;
   uint8_t* s_al = s_ah + abytes;
@@ -235,19 +257,42 @@ k_dw_tc(const DwTc p) {
       const float2* gs = p.gyh + ((size_t)(live ? b : 0) * p.Co) * p.Kt + k;
       // the previous round of MMAs must have finished reading the operand images before they are overwritten
       if (pending) { mbar_wait(&bar, phase); phase ^= 1u; pending = false; }
-      for (int i = part; i < p.Ci; i += nparts) {
-        const float2 v = live ? __ldg(xs + (size_t)i * p.Kt) : make_float2(0.f, 0.f);
-        const uint32_t o0 = dw_off(2 * i, bb), o1 = dw_off(2 * i + 1, bb);
-        const float hx = tf32_rna(v.x), hy = tf32_rna(v.y);
-        *(float*)(s_ah + o0) = hx; *(float*)(s_ah + o1) = hy;
-        *(float*)(s_al + o0) = tf32_rna(v.x - hx); *(float*)(s_al + o1) = tf32_rna(v.y - hy);
+      // gathers in batches of 8 (all in flight before the first shared-memory store)
+      for (int i0 = part; i0 < p.Ci; i0 += 8 * nparts) {
+        float2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int i = i0 + u * nparts;
+          v[u] = (live && i < p.Ci) ? __ldg(xs + (size_t)i * p.Kt) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int i = i0 + u * nparts;
+          if (i < p.Ci) {
+            const uint32_t o0 = dw_off(2 * i, bb), o1 = dw_off(2 * i + 1, bb);
+            const float hx = tf32_rna(v[u].x), hy = tf32_rna(v[u].y);
+            *(float*)(s_ah + o0) = hx; *(float*)(s_ah + o1) = hy;
+            *(float*)(s_al + o0) = tf32_rna(v[u].x - hx); *(float*)(s_al + o1) = tf32_rna(v[u].y - hy);
+          }
+        }
       }
-      for (int o = part; o < p.Co; o += nparts) {
-        const float2 v = live ? __ldg(gs + (size_t)o * p.Kt) : make_float2(0.f, 0.f);
-        const uint32_t o0 = dw_off(2 * o, bb), o1 = dw_off(2 * o + 1, bb);
-        const float hx = tf32_rna(v.x), hy = tf32_rna(v.y);
-        *(float*)(s_bh + o0) = hx; *(float*)(s_bh + o1) = hy;
-        *(float*)(s_bl + o0) = tf32_rna(v.x - hx); *(float*)(s_bl + o1) = tf32_rna(v.y - hy);
+      for (int o0c = part; o0c < p.Co; o0c += 8 * nparts) {
+        float2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int o = o0c + u * nparts;
+          v[u] = (live && o < p.Co) ? __ldg(gs + (size_t)o * p.Kt) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int o = o0c + u * nparts;
+          if (o < p.Co) {
+            const uint32_t o0 = dw_off(2 * o, bb), o1 = dw_off(2 * o + 1, bb);
+            const float hx = tf32_rna(v[u].x), hy = tf32_rna(v[u].y);
+            *(float*)(s_bh + o0) = hx; *(float*)(s_bh + o1) = hy;
+            *(float*)(s_bl + o0) = tf32_rna(v[u].x - hx); *(float*)(s_bl + o1) = tf32_rna(v[u].y - hy);
+          }
+        }
       }
       fence_proxy_async();
       __syncthreads();
@@ -330,8 +375,18 @@ int b2no_tc_mix(const b2no_plan* p, int mode, const float* in, const b2no_weight
   B2NO_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   if ((int)smem > max_smem) return 1;
   B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_mix_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = q.Kt < b2no_sm_count() ? q.Kt : b2no_sm_count();
-  k_mix_tc<<<grid, kMixThreads, smem, st>>>(q);
+  // two CTAs per SM when TMEM (<= 256 columns each) and shared memory allow: the kernel is a chain of gather latencies
+  const int per_sm = (2 * q.Kp + q.Np <= 256 && smem <= 100 * 1024) ? 2 : 1;
+  const long items = (long)q.Kt * ((batch + 127) / 128);
+  long grid = (long)b2no_sm_count() * per_sm;
+  if (grid > items) grid = items;
+  // residency = TMEM budget: ask for enough shared memory that no more than per_sm CTAs fit an SM (a third CTA would sit
+  // in tcgen05.alloc holding its slot)
+  size_t smem_req = smem;
+  const size_t floor_req = per_sm == 2 ? 100 * 1024 : 120 * 1024;
+  if (smem_req < floor_req) smem_req = floor_req;
+  B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_mix_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req));
+  k_mix_tc<<<(unsigned)grid, kMixThreads, smem_req, st>>>(q);
   B2NO_LAUNCH_CHECK();
   b2no_tc_count_launch();
   return 0;
@@ -346,14 +401,24 @@ int b2no_tc_mix_dw(const b2no_plan* p, const float* xh, const float* gyh, const 
   q.accumulate = accumulate; q.npass = b2no_tc_passes();
   q.xh = (const float2*)xh; q.gyh = (const float2*)gyh; q.w = *dw; q.mm = make_mode_map(p);
   if (2 * ci > 128 || q.Np > 256) return 1;
-  const size_t smem = 2 * (size_t)16 * kDwSbo + 2 * (size_t)(q.Np / 8) * kDwSbo + 1024;
+  q.Ga = (2 * ci + 7) / 8;
+  // the M = 128 MMA reads 16 row groups from the A base: keep them inside the allocation
+  size_t smem = 2 * (size_t)q.Ga * kDwSbo + 2 * (size_t)(q.Np / 8) * kDwSbo;
+  if (smem < 2 * (size_t)q.Ga * kDwSbo + 16 * (size_t)kDwSbo) smem = 2 * (size_t)q.Ga * kDwSbo + 16 * (size_t)kDwSbo;
+  smem += 1024;
   int dev = 0, max_smem = 0;
   B2NO_CHECK_CUDA(cudaGetDevice(&dev));
   B2NO_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   if ((int)smem > max_smem) return 1;
   B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_dw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = q.Kt < b2no_sm_count() ? q.Kt : b2no_sm_count();
-  k_dw_tc<<<grid, kMixThreads, smem, st>>>(q);
+  const int per_sm = (q.Np <= 256 && smem <= 100 * 1024) ? 2 : 1;
+  int grid = b2no_sm_count() * per_sm;
+  if (grid > q.Kt) grid = q.Kt;
+  size_t smem_req = smem;
+  const size_t floor_req = per_sm == 2 ? 100 * 1024 : 120 * 1024;
+  if (smem_req < floor_req) smem_req = floor_req;
+  B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_dw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req));
+  k_dw_tc<<<grid, kMixThreads, smem_req, st>>>(q);
   B2NO_LAUNCH_CHECK();
   b2no_tc_count_launch();
   return 0;

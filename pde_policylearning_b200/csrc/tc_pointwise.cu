@@ -441,7 +441,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
 //   S[b,o,h,ky] = sum_kx M[kx][h] * spec[b][o][kx][ky];   q = 2 ky -> Re S, 2 ky + 1 -> Im S
 // One block per (sample, group of HB rows): the sample's spectrum is staged in shared memory once.
 constexpr int kInvHB = 32;
-template <int KXM>   // compile-time bound on the kept rows Kx (register array size)
+template <int KXM, bool PAIR>   // KXM: compile-time bound on the kept rows Kx (register array size); PAIR: two modes per thread
 __global__ void __launch_bounds__(256)
 k_inv_h(const float2* __restrict__ spec, const float2* __restrict__ M, float* __restrict__ ahi, float* __restrict__ alo,
         int Co, int Np, int Kx, int H, int Ky, int Qp) {
@@ -459,42 +459,72 @@ k_inv_h(const float2* __restrict__ spec, const float2* __restrict__ M, float* __
   }
   __syncthreads();
   const int ng = Np >> 3, nq = Qp >> 2;
-  const int per_row = nq * ng * 8;                     // (kq, og, o8): the two ky of a q-quad (4 floats = 16 B) per thread
   const int rows = H - h0 < kInvHB ? H - h0 : kInvHB;
-  // A thread owns one (kq, og, o8) slot = TWO modes ky = 2 kq, 2 kq + 1 of one channel: its 2 Kx spectrum values do not
-  // depend on the row, so they are read once into registers; every row then costs Kx x (one broadcast LDS.64 of M + four
-  // packed FFMA2) for two complex outputs, stored as one 16-byte word.  (One output per thread and scalar FMAs made this
-  // kernel issue-bound: 5 instructions per complex MAC, 60 us at the RNO shape.)
+  // A thread owns one output slot; its Kx spectrum values do not depend on the row, so they are read once into registers and
+  // every row then costs Kx x (one broadcast LDS.64 of M + packed FFMA2s):
   //   acc_a += Re M * v,  acc_b += Im M * v   ->   S = (acc_a.x - acc_b.y) + i (acc_a.y + acc_b.x)
-  for (int e = threadIdx.x; e < per_row; e += 256) {
-    const int o8 = e & 7;
-    const int r = e >> 3;
-    const int og = r % ng, kq = r / ng;
-    const int ky0 = kq * 2, o = og * 8 + o8;
-    const bool valid0 = o < Co && ky0 < Ky, valid1 = o < Co && ky0 + 1 < Ky;
-    float2 v0[KXM], v1[KXM];
-#pragma unroll
-    for (int kx = 0; kx < KXM; kx++) {
-      v0[kx] = (valid0 && kx < Kx) ? s_spec[o * stride + kx * Ky + ky0] : make_float2(0.f, 0.f);
-      v1[kx] = (valid1 && kx < Kx) ? s_spec[o * stride + kx * Ky + ky0 + 1] : make_float2(0.f, 0.f);
-    }
-    const size_t off0 = ((size_t)b * H + h0) * Qp * Np + (size_t)kq * ng * 32 + og * 32 + o8 * 4;
-    for (int hl = 0; hl < rows; hl++) {
-      float2 a0 = make_float2(0.f, 0.f), b0 = a0, a1 = a0, b1 = a0;
+  // PAIR: the slot is (kq, og, o8) = TWO modes ky = 2 kq, 2 kq + 1 of one channel, stored as one 16-byte word (half the
+  // instructions per complex MAC; used when there are enough slots to keep all 256 threads busy, e.g. the RNO shape -- one
+  // output per thread with scalar FMAs made this kernel issue-bound there: 60 us).
+  if (PAIR) {
+    const int per_row = nq * ng * 8;
+    for (int e = threadIdx.x; e < per_row; e += 256) {
+      const int o8 = e & 7;
+      const int r = e >> 3;
+      const int og = r % ng, kq = r / ng;
+      const int ky0 = kq * 2, o = og * 8 + o8;
+      const bool valid0 = o < Co && ky0 < Ky, valid1 = o < Co && ky0 + 1 < Ky;
+      float2 v0[KXM], v1[KXM];
 #pragma unroll
       for (int kx = 0; kx < KXM; kx++) {
-        if (kx < Kx) {
-          const float2 m = s_m[kx * kInvHB + hl];
-          const float2 mr = make_float2(m.x, m.x), mi = make_float2(m.y, m.y);
-          a0 = __ffma2_rn(mr, v0[kx], a0);
-          b0 = __ffma2_rn(mi, v0[kx], b0);
-          a1 = __ffma2_rn(mr, v1[kx], a1);
-          b1 = __ffma2_rn(mi, v1[kx], b1);
-        }
+        v0[kx] = (valid0 && kx < Kx) ? s_spec[o * stride + kx * Ky + ky0] : make_float2(0.f, 0.f);
+        v1[kx] = (valid1 && kx < Kx) ? s_spec[o * stride + kx * Ky + ky0 + 1] : make_float2(0.f, 0.f);
       }
-      const size_t off = off0 + (size_t)hl * Qp * Np;
-      // fp32; k_pw_tc's converter warps make the hi / lo split
-      *reinterpret_cast<float4*>(ahi + off) = make_float4(a0.x - b0.y, a0.y + b0.x, a1.x - b1.y, a1.y + b1.x);
+      const size_t off0 = ((size_t)b * H + h0) * Qp * Np + (size_t)kq * ng * 32 + og * 32 + o8 * 4;
+      for (int hl = 0; hl < rows; hl++) {
+        float2 a0 = make_float2(0.f, 0.f), b0 = a0, a1 = a0, b1 = a0;
+#pragma unroll
+        for (int kx = 0; kx < KXM; kx++) {
+          if (kx < Kx) {
+            const float2 m = s_m[kx * kInvHB + hl];
+            const float2 mr = make_float2(m.x, m.x), mi = make_float2(m.y, m.y);
+            a0 = __ffma2_rn(mr, v0[kx], a0);
+            b0 = __ffma2_rn(mi, v0[kx], b0);
+            a1 = __ffma2_rn(mr, v1[kx], a1);
+            b1 = __ffma2_rn(mi, v1[kx], b1);
+          }
+        }
+        const size_t off = off0 + (size_t)hl * Qp * Np;
+        // fp32; k_pw_tc's converter warps make the hi / lo split
+        *reinterpret_cast<float4*>(ahi + off) = make_float4(a0.x - b0.y, a0.y + b0.x, a1.x - b1.y, a1.y + b1.x);
+      }
+    }
+  } else {
+    const int per_row = nq * ng * 16;                    // (kq, og, o8, l0): one complex output each
+    for (int e = threadIdx.x; e < per_row; e += 256) {
+      const int l0 = e & 1, o8 = (e >> 1) & 7;
+      const int r = e >> 4;
+      const int og = r % ng, kq = r / ng;
+      const int ky = kq * 2 + l0, o = og * 8 + o8;
+      const bool valid = o < Co && ky < Ky;
+      float2 v[KXM];
+#pragma unroll
+      for (int kx = 0; kx < KXM; kx++)
+        v[kx] = (valid && kx < Kx) ? s_spec[o * stride + kx * Ky + ky] : make_float2(0.f, 0.f);
+      const size_t off0 = ((size_t)b * H + h0) * Qp * Np + (size_t)kq * ng * 32 + og * 32 + o8 * 4 + l0 * 2;
+      for (int hl = 0; hl < rows; hl++) {
+        float2 a0 = make_float2(0.f, 0.f), b0 = a0;
+#pragma unroll
+        for (int kx = 0; kx < KXM; kx++) {
+          if (kx < Kx) {
+            const float2 m = s_m[kx * kInvHB + hl];
+            a0 = __ffma2_rn(make_float2(m.x, m.x), v[kx], a0);
+            b0 = __ffma2_rn(make_float2(m.y, m.y), v[kx], b0);
+          }
+        }
+        const size_t off = off0 + (size_t)hl * Qp * Np;
+        *reinterpret_cast<float2*>(ahi + off) = make_float2(a0.x - b0.y, a0.y + b0.x);
+      }
     }
   }
 }
@@ -626,11 +656,16 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
     const size_t smem = ((size_t)channels * (plan->K[0] * plan->K[1] + 1) + (size_t)plan->K[0] * kInvHB) * sizeof(float2);
     if (smem > 200 * 1024) return 1;
     dim3 grid((unsigned)((n[0] + kInvHB - 1) / kInvHB), (unsigned)batch);
+    const bool pair = (p.Qp / 4) * (p.Np / 8) * 8 >= 256;      // enough two-mode slots for every thread of the block
+#define INVH_LAUNCH1(KXM, PAIR)                                                                                         \
+  do {                                                                                                                  \
+    if (smem > 48 * 1024) B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_inv_h<KXM, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_inv_h<KXM, PAIR><<<grid, 256, smem, st>>>((const float2*)spec, M, (float*)p.ahi, (float*)p.alo, channels, p.Np, plan->K[0], n[0], \
+                                                plan->K[1], p.Qp);                                                      \
+  } while (0)
 #define INVH_LAUNCH(KXM)                                                                                                \
   do {                                                                                                                  \
-    if (smem > 48 * 1024) B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_inv_h<KXM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_inv_h<KXM><<<grid, 256, smem, st>>>((const float2*)spec, M, (float*)p.ahi, (float*)p.alo, channels, p.Np, plan->K[0], n[0], \
-                                          plan->K[1], p.Qp);                                                            \
+    if (pair) INVH_LAUNCH1(KXM, true); else INVH_LAUNCH1(KXM, false);                                                   \
   } while (0)
     const int kx = plan->K[0];
     if (kx <= 8) INVH_LAUNCH(8);
@@ -639,6 +674,7 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
     else if (kx <= 24) INVH_LAUNCH(24);
     else if (kx <= 32) INVH_LAUNCH(32);
     else return 1;
+#undef INVH_LAUNCH1
 #undef INVH_LAUNCH
     B2NO_LAUNCH_CHECK();
   }
