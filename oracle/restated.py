@@ -162,7 +162,7 @@ def rno2d_forward(sd, x, modes1, modes2, width, recurrent_index=0, layer_num=1, 
         for i in range(layer_num):
             h = states[i]
             if h is None:
-                h = torch.zeros(t.shape[0], width, t.shape[3], t.shape[4], dtype=dt) + sd[f"layers.{i}.bias_h"].to(dt)
+                h = torch.zeros(t.shape[0], width, t.shape[3], t.shape[4], dtype=dt, device=t.device) + sd[f"layers.{i}.bias_h"].to(dt)
             outs = []
             for s in range(t.shape[1]):
                 h = rno_cell(sd, f"layers.{i}.cell.", t[:, s], h, modes1, modes2)
@@ -203,10 +203,10 @@ def pino_spectral_conv3d(x, w1, w2, w3, w4, m1, m2, m3):
     Co = w1.shape[1]
     xf = torch.fft.rfftn(x, dim=[2, 3, 4])
     zd = min(xf.shape[4], m3)
-    out = torch.zeros(B, Co, xf.shape[2], xf.shape[3], m3, dtype=cdt)
+    out = torch.zeros(B, Co, xf.shape[2], xf.shape[3], m3, dtype=cdt, device=x.device)
 
     def corner(sl1, sl2, w):
-        c = torch.zeros(B, x.shape[1], m1, m2, m3, dtype=cdt)
+        c = torch.zeros(B, x.shape[1], m1, m2, m3, dtype=cdt, device=x.device)
         c[..., :zd] = xf[:, :, sl1, sl2, :zd]
         return torch.einsum("bixyz,ioxyz->boxyz", c, w.to(cdt))
 
@@ -224,7 +224,7 @@ def pino_spectral_conv2d(x, w1, w2, m1, m2):
     cdt = torch.complex128 if x.dtype == torch.float64 else torch.complex64
     B, Co = x.shape[0], w1.shape[1]
     xf = torch.fft.rfftn(x, dim=[2, 3])
-    out = torch.zeros(B, Co, x.size(-2), x.size(-1) // 2 + 1, dtype=cdt)
+    out = torch.zeros(B, Co, x.size(-2), x.size(-1) // 2 + 1, dtype=cdt, device=x.device)
     out[:, :, :m1, :m2] = torch.einsum("bixy,ioxy->boxy", xf[:, :, :m1, :m2], w1.to(cdt))
     out[:, :, -m1:, :m2] = torch.einsum("bixy,ioxy->boxy", xf[:, :, -m1:, :m2], w2.to(cdt))
     return torch.fft.irfftn(out, s=(x.size(-2), x.size(-1)), dim=[2, 3])

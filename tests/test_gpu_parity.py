@@ -987,3 +987,74 @@ def test_tile_kernel_single_a_buffer(ci, ci2, co):
     y = ops.pointwise(B, co, grid, dev, ops.make_epilogue(bias=bias.to(dev), pw_w=w.to(dev), pw_x=x.to(dev), act="gelu", **kw))
     assert ops.tensor_core_launches() == n0 + 1, "tile kernel did not run"
     assert rel(y, torch.nn.functional.gelu(z64)) < TOL
+
+
+def _sd64(m):
+    sd = {}
+    for k, v in m.state_dict().items():
+        v = v.detach()
+        sd[k] = (v.to(torch.complex128) if v.is_complex() else v.double()).requires_grad_(True)
+    return sd
+
+
+def test_cfg3_rno_full_size_vs_restated():
+    """BASELINE config 3 shape: RNO2dObserver(12,12,34, layer_num 1) on B = 256 trajectories of 32x32 planes (T = 4 frames of
+    the 100: 7 recurrent cell steps + 4 regressor calls, every kernel at its bench shape incl. the tensor-core mixing),
+    `.eval()`; output, loss and every parameter gradient against the restated reference algorithm in float64."""
+    import pde_policylearning_b200 as P
+    from oracle import restated as rs
+    dev = _dev()
+    torch.manual_seed(13)
+    m = P.RNO2dObserver(12, 12, 34, 0, layer_num=1).to(dev).eval()
+    B, T = 256, 4
+    x = torch.randn(B, T, 32, 32, 1, device=dev)
+    tgt = torch.randn(B, 32, 32, 1, device=dev)
+    out = m(x)
+    loss = P.rel_l2_loss(out.reshape(B, -1), tgt.reshape(B, -1), size_average=False)
+    names = [n for n, _ in m.named_parameters()]
+    gs = torch.autograd.grad(loss, [p for _, p in m.named_parameters()])
+    sd = _sd64(m)
+    out64 = rs.rno2d_forward(sd, x.double(), 12, 12, 34, recurrent_index=0, layer_num=1)
+    loss64 = rs.lp_rel(out64.reshape(B, -1), tgt.double().reshape(B, -1), size_average=False)
+    gs64 = torch.autograd.grad(loss64, [sd[n] for n in names])
+    eo = rel(out, out64)
+    worst = max(rel(a, b) for a, b in zip(gs, gs64))
+    print(f"cfg3 full size: output {eo:.2e}, loss {abs(loss.item() - loss64.item()) / abs(loss64.item()):.2e}, worst gradient {worst:.2e}")
+    assert eo < 2e-5, eo
+    assert abs(loss.item() - loss64.item()) < 1e-5 * abs(loss64.item())
+    for n, a, b in zip(names, gs, gs64):
+        assert rel(a, b) < 2e-4, (n, rel(a, b))
+
+
+def test_cfg4_pino_full_size_vs_restated():
+    """BASELINE config 4 shape: PINObserver2d (4 x 64 channels, modes 8, fc 128, pad 0.0625) on ONE 64x64x65 sample with
+    the training loss 5 data + f + ic (train_pino.py:87-107; fused residual-loss kernels, fused head); output, the three
+    loss terms and every parameter gradient against the restated reference algorithm in float64."""
+    import pde_policylearning_b200 as P
+    from oracle import restated as rs
+    dev = _dev()
+    torch.manual_seed(14)
+    m = P.PINObserver2d(modes1=[8] * 4, modes2=[8] * 4, modes3=[8] * 4, fc_dim=128, layers=[64] * 5, act="gelu",
+                        pad_ratio=0.0625).to(dev)
+    S, T = 64, 65
+    a_in = torch.randn(1, S, S, T, 4, device=dev)
+    u = torch.randn(1, S, S, T, device=dev)
+    re = torch.tensor([250.0], device=dev)
+    forcing = P.get_forcing(S, device=dev)
+    out = m(a_in, re)
+    loss = P.pino_training_loss(m, a_in, re, u, forcing, 5.0, 1.0, 1.0, 0.5)
+    names = [n for n, _ in m.named_parameters()]
+    gs = torch.autograd.grad(loss, [p for _, p in m.named_parameters()])
+    sd = _sd64(m)
+    out64 = rs.pinobserver2d_forward(sd, a_in.double(), re.double(), [8] * 4, [8] * 4, [8] * 4, [64] * 5, 0.0625)
+    o4 = out64.reshape(1, S, S, T)
+    lic64, lf64 = rs.channelflow_pino_loss(o4, a_in[:, :, :, 0, -1].double(), forcing.double(), 1.0 / re.double(), 0.5)
+    loss64 = 5.0 * rs.lp_rel(o4, u.double()) + lf64 + lic64
+    gs64 = torch.autograd.grad(loss64, [sd[n] for n in names])
+    eo = rel(out, out64)
+    worst = max(rel(a, b) for a, b in zip(gs, gs64))
+    print(f"cfg4 full size: output {eo:.2e}, loss {abs(loss.item() - loss64.item()) / abs(loss64.item()):.2e}, worst gradient {worst:.2e}")
+    assert eo < 2e-5, eo
+    assert abs(loss.item() - loss64.item()) < 2e-5 * abs(loss64.item())
+    for n, a, b in zip(names, gs, gs64):
+        assert rel(a, b) < 2e-4, (n, rel(a, b))
