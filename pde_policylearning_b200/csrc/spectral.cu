@@ -89,11 +89,77 @@ static int launch_r2c(const float* x, float* out, const float* tab, long R, int 
   return 0;
 }
 
+// =============================================================================================
+// k_r2c_rows: the same stage for few kept modes (q2 <= 16, e.g. the PINO layer: 73 samples -> 8 modes).  A warp stages 8
+// consecutive rows (8 N contiguous floats, 128-bit loads) in shared memory; lane l then owns row l / 4 and QL of its q2
+// outputs: per sample one broadcast LDS of x, one vector LDS of the transposed table row and QL FMAs -- no cross-lane
+// reduction at all.  (k_r2c_last spends as many instructions on its transposing butterfly as on FMAs: ncu showed it
+// issue-bound at 70 % with FSEL + SHFL + FADD = 32 % of the instructions, profiles/r02_d_ncu_pino_r2c.txt.)
+// =============================================================================================
+template <int QL>
+__global__ void __launch_bounds__(256)
+k_r2c_rows(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ tab, long R, int N, int npad, int q2) {
+  extern __shared__ float s_dyn[];
+  constexpr int Q2P = 4 * QL;
+  float* s_tabT = s_dyn;                              // [N][Q2P]
+  float* s_rows = s_dyn + (size_t)N * Q2P;            // [8 warps][8 N]
+  for (int i = threadIdx.x; i < N * Q2P; i += 256) {
+    const int n = i / Q2P, q = i - n * Q2P;
+    s_tabT[i] = q < q2 ? tab[(size_t)q * npad + n] : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* rows = s_rows + (size_t)warp * 8 * N;
+  const int r = lane >> 2, q0 = (lane & 3) * QL;
+  const long ngroups = R >> 3;                        // R % 8 == 0 (checked by the launcher)
+  for (long g = (long)blockIdx.x * 8 + warp; g < ngroups; g += (long)gridDim.x * 8) {
+    const float4* src = reinterpret_cast<const float4*>(x + (g << 3) * N);
+    for (int i = lane; i < 2 * N; i += 32) reinterpret_cast<float4*>(rows)[i] = __ldg(src + i);
+    __syncwarp();
+    float acc[QL];
+#pragma unroll
+    for (int i = 0; i < QL; i++) acc[i] = 0.f;
+    const float* xr = rows + r * N;
+#pragma unroll 4
+    for (int n = 0; n < N; n++) {
+      const float xv = xr[n];
+      const float* t = s_tabT + n * Q2P + q0;
+#pragma unroll
+      for (int i = 0; i < QL; i++) acc[i] = fmaf(xv, t[i], acc[i]);
+    }
+    float* dst = out + ((g << 3) + r) * q2 + q0;
+#pragma unroll
+    for (int i = 0; i < QL; i++)
+      if (q0 + i < q2) dst[i] = acc[i];
+    __syncwarp();
+  }
+}
+
+template <int QL>
+static int launch_r2c_rows(const float* x, float* out, const float* tab, long R, int N, int npad, int q2, cudaStream_t st) {
+  const size_t smem = ((size_t)N * 4 * QL + (size_t)8 * 8 * N) * sizeof(float);
+  if (smem > 48 * 1024)
+    B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_r2c_rows<QL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long ngroups = R / 8;
+  long blocks = (ngroups + 7) / 8;
+  const long cap = (long)b2no_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_r2c_rows<QL><<<(unsigned)blocks, 256, smem, st>>>(x, out, tab, R, N, npad, q2);
+  B2NO_LAUNCH_CHECK();
+  return 0;
+}
+
 static int run_r2c(const b2no_plan* p, int which, const float* x, float* out, long R, cudaStream_t st) {
   const int d = p->g.ndim;
   const int N = which == 0 ? p->g.nin[d - 1] : p->g.nout[d - 1];
   const int npad = which == 0 ? p->npad_in : p->npad_out;
   const float* tab = which == 0 ? p->t_in : p->t_out;
+  if (R % 8 == 0 && p->q2 <= 16 && N >= 8 && N <= 512 && (((uintptr_t)x) & 15) == 0) {
+    if (p->q2 <= 4) return launch_r2c_rows<1>(x, out, tab, R, N, npad, p->q2, st);
+    if (p->q2 <= 8) return launch_r2c_rows<2>(x, out, tab, R, N, npad, p->q2, st);
+    return launch_r2c_rows<4>(x, out, tab, R, N, npad, p->q2, st);
+  }
   switch (p->qc) {
     case 4: return launch_r2c<4>(x, out, tab, R, N, npad, p->q2, p->nchunk, st);
     case 8: return launch_r2c<8>(x, out, tab, R, N, npad, p->q2, p->nchunk, st);
@@ -476,6 +542,7 @@ k_c2r_fused(const float2* __restrict__ spec, float* __restrict__ y, const float*
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_nc = (N + 32 * NPT - 1) / (32 * NPT);
   const long n_items = (long)B * RPI * n_nc * n_ot;
+  const bool plain = !e.add && !e.preact && !e.mul && !e.dz && !e.gate_z && e.act == B2NO_ACT_NONE;
   for (long item = (long)blockIdx.x * 8 + warp; item < n_items; item += (long)gridDim.x * 8) {
     const int ot = (int)(item % n_ot);
     long t = item / n_ot;
@@ -556,6 +623,16 @@ k_c2r_fused(const float2* __restrict__ spec, float* __restrict__ y, const float*
       const int o = o0 + oo;
       if (o < Co) {
         const float bv = e.bias ? __ldg(e.bias + o) : 0.f;
+        if (plain) {
+          // transform (+ bias) only: one add and one store per output.  (The generic epilogue below costs ~120 instructions
+          // per output -- pointer tests, 64-bit index arithmetic, the activation switch -- and made the 3-D last stage
+          // instruction-bound: 1.13 ms for 306 MB, ncu profiles/r02_d_ncu_pino_c2r.txt.)
+          float* yr = y + ((size_t)b * Co + o) * P + (size_t)r * N + nbase + lane;
+#pragma unroll
+          for (int j = 0; j < NPT; j++)
+            if (valid[j]) yr[32 * j] = acc[oo][j] + bv;
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < NPT; j++) {
           if (valid[j]) {
@@ -603,6 +680,28 @@ static int run_c2r(const float2* spec, float* y, const float* tab, const EpiDev&
   if (N <= 64) return launch_c2r<2, OT>(spec, y, tab, e, B, Co, RPI, N, P, Kd, npad, st);
   if (N <= 96) return launch_c2r<3, OT>(spec, y, tab, e, B, Co, RPI, N, P, Kd, npad, st);
   return launch_c2r<4, OT>(spec, y, tab, e, B, Co, RPI, N, P, Kd, npad, st);
+}
+
+// n x n identity matrices on the device, one per (device, n), created on first use (never inside a graph capture: the
+// first call of every shape is an eager warm-up, as for the plans) and kept for the life of the process
+__global__ void k_fill_identity(float* m, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * n) m[i] = (i / n == i % n) ? 1.0f : 0.0f;
+}
+static const float* identity_matrix(int n, cudaStream_t st) {
+  static float* cache[8][129] = {};
+  int dev = 0;
+  if (n < 1 || n > 128 || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 8) return nullptr;
+  if (!cache[dev][n]) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;
+    float* m = nullptr;
+    if (cudaMalloc(&m, (size_t)n * n * sizeof(float)) != cudaSuccess) return nullptr;
+    k_fill_identity<<<(n * n + 255) / 256, 256, 0, st>>>(m, n);
+    if (cudaGetLastError() != cudaSuccess) { cudaFree(m); return nullptr; }
+    cache[dev][n] = m;
+  }
+  return cache[dev][n];
 }
 
 extern "C" int b2no_dft_inverse(const b2no_plan* p, int which, const float* spec, float* y, float* work,
@@ -682,8 +781,22 @@ extern "C" int b2no_dft_inverse(const b2no_plan* p, int which, const float* spec
     rc = run_c2r(A, T, tab, e0, batch, channels, (long)n[0] * n[1], n[2], P, Kl, npad, st);
     if (rc) return rc;
     b2no_epilogue epi2 = *epi;
-    epi2.add = T;
+    // T enters the tile kernel as a SECOND 1x1 operand with identity weights when that slot is free: it then arrives
+    // through the TMA ring like x and is added by the tensor core, and the specialised epilogues (bias / GELU + saved
+    // pre-activation) stay eligible.  Through `add` it would take the generic epilogue, whose per-thread loads held the
+    // PINO layer at 2.4 TB/s (499 us per pass, profiles/r02_c_pino_step_breakdown.txt).
+    const float* ident = (!epi->pw2_w && channels <= 128) ? identity_matrix(channels, st) : nullptr;
+    if (ident) {
+      epi2.pw2_w = ident; epi2.pw2_x = T; epi2.pw2_ci = channels; epi2.pw2_transposed = 0;
+    } else {
+      epi2.add = T;
+    }
     rc = b2no_tc_pointwise(nullptr, which, nullptr, y, nullptr, batch, channels, P, &epi2, st);
+    if (rc == 1 && ident) {                    // shape without the two-operand tile kernel: T through `add` instead
+      epi2 = *epi;
+      epi2.add = T;
+      rc = b2no_tc_pointwise(nullptr, which, nullptr, y, nullptr, batch, channels, P, &epi2, st);
+    }
     if (rc != 1) return rc;
     EpiDev e2 = e;
     e2.add = T;
