@@ -673,9 +673,119 @@ static int launch_c2r(const float2* spec, float* y, const float* tab, const EpiD
   return 0;
 }
 
+// =============================================================================================
+// k_c2r_plain: the last inverse stage alone (+ bias) for K_last = 8 kept modes -- the PINO layer, whose 1x1 conv and
+// activation run on the tensor-core tile kernel.  Same item decomposition as k_c2r_fused (warp = one row x 16 channels),
+// but the item's 16 x 8 spectrum values are fetched with FOUR coalesced loads per lane (each value once per warp, the
+// next item's loads issued before this item's arithmetic) and handed round by shuffles, instead of 128 warp-uniform
+// loads in eight dependent rounds: ncu showed the fused kernel latency-bound at 30 % issue utilisation, 0.8 TB/s.
+// =============================================================================================
+template <int NPT>
+__global__ void __launch_bounds__(256)
+k_c2r_plain8(const float2* __restrict__ spec, float* __restrict__ y, const float* __restrict__ tab,
+             const float* __restrict__ bias, int B, int Co, long RPI, int N, long P, int npad) {
+  constexpr int OT = 16, KD = 8;
+  extern __shared__ float s_tab8[];                   // [2 KD][npad]
+  for (int i = threadIdx.x; i < 2 * KD * npad; i += blockDim.x) s_tab8[i] = tab[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_ot = (Co + OT - 1) / OT;
+  const int n_nc = (N + 32 * NPT - 1) / (32 * NPT);
+  const long n_items = (long)B * RPI * n_nc * n_ot;
+  const size_t ostride = (size_t)RPI * KD;
+  auto fetch = [&](long item, float2 (&v)[4]) {
+    const int ot = (int)(item % n_ot);
+    long t = item / n_ot / n_nc;
+    const long r = t % RPI;
+    const int b = (int)(t / RPI);
+    const float2* sp = spec + (((size_t)b * Co + ot * OT) * RPI + r) * KD;
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      const int idx = lane + 32 * m, oo = idx >> 3, k = idx & 7;
+      v[m] = (ot * OT + oo < Co) ? __ldg(sp + oo * ostride + k) : make_float2(0.f, 0.f);
+    }
+  };
+  long item = (long)blockIdx.x * 8 + warp;
+  const long step = (long)gridDim.x * 8;
+  float2 cur[4], nxt[4];
+  if (item < n_items) fetch(item, cur);
+  for (; item < n_items; item += step) {
+    if (item + step < n_items) fetch(item + step, nxt);
+    const int ot = (int)(item % n_ot);
+    long t = item / n_ot;
+    const int nc = (int)(t % n_nc);
+    t /= n_nc;
+    const long r = t % RPI;
+    const int b = (int)(t / RPI);
+    const int o0 = ot * OT, nbase = nc * 32 * NPT;
+    float acc[OT][NPT];
+#pragma unroll
+    for (int oo = 0; oo < OT; oo++)
+#pragma unroll
+      for (int j = 0; j < NPT; j++) acc[oo][j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KD; k++) {
+      float tr[NPT], ti[NPT];
+#pragma unroll
+      for (int j = 0; j < NPT; j++) {
+        const int n = nbase + lane + 32 * j;            // < npad by construction
+        tr[j] = s_tab8[(size_t)(2 * k) * npad + n];
+        ti[j] = s_tab8[(size_t)(2 * k + 1) * npad + n];
+      }
+#pragma unroll
+      for (int oo = 0; oo < OT; oo++) {
+        const int idx = oo * KD + k;
+        const float vx = __shfl_sync(0xffffffffu, cur[idx >> 5].x, idx & 31);
+        const float vy = __shfl_sync(0xffffffffu, cur[idx >> 5].y, idx & 31);
+#pragma unroll
+        for (int j = 0; j < NPT; j++) acc[oo][j] = fmaf(vx, tr[j], fmaf(vy, ti[j], acc[oo][j]));
+      }
+    }
+#pragma unroll
+    for (int oo = 0; oo < OT; oo++) {
+      const int o = o0 + oo;
+      if (o < Co) {
+        const float bv = bias ? __ldg(bias + o) : 0.f;
+        float* yr = y + ((size_t)b * Co + o) * P + (size_t)r * N + nbase + lane;
+#pragma unroll
+        for (int j = 0; j < NPT; j++) {
+          const int n = nbase + lane + 32 * j;
+          if (n < N) yr[32 * j] = acc[oo][j] + bv;
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; m++) cur[m] = nxt[m];
+  }
+}
+
+template <int NPT>
+static int launch_c2r_plain8(const float2* spec, float* y, const float* tab, const float* bias, int B, int Co, long RPI,
+                             int N, long P, int npad, cudaStream_t st) {
+  const size_t smem = (size_t)16 * npad * sizeof(float);
+  if (smem > 48 * 1024)
+    B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_c2r_plain8<NPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int n_ot = (Co + 15) / 16, n_nc = (N + 32 * NPT - 1) / (32 * NPT);
+  const long n_items = (long)B * RPI * n_nc * n_ot;
+  long blocks = (n_items + 7) / 8;
+  const long cap = (long)b2no_sm_count() * 6;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_c2r_plain8<NPT><<<(unsigned)blocks, 256, smem, st>>>(spec, y, tab, bias, B, Co, RPI, N, P, npad);
+  B2NO_LAUNCH_CHECK();
+  return 0;
+}
+
 static int run_c2r(const float2* spec, float* y, const float* tab, const EpiDev& e, int B, int Co, long RPI, int N,
                    long P, int Kd, int npad, cudaStream_t st) {
   constexpr int OT = 16;
+  const bool plain = !e.add && !e.preact && !e.mul && !e.dz && !e.gate_z && e.act == B2NO_ACT_NONE;
+  if (spec && plain && e.pw_ci == 0 && e.pw2_ci == 0 && Kd == 8 && npad * 16 * 4 <= 160 * 1024) {
+    if (N <= 32) return launch_c2r_plain8<1>(spec, y, tab, e.bias, B, Co, RPI, N, P, npad, st);
+    if (N <= 64) return launch_c2r_plain8<2>(spec, y, tab, e.bias, B, Co, RPI, N, P, npad, st);
+    if (N <= 96) return launch_c2r_plain8<3>(spec, y, tab, e.bias, B, Co, RPI, N, P, npad, st);
+    if (N <= 128) return launch_c2r_plain8<4>(spec, y, tab, e.bias, B, Co, RPI, N, P, npad, st);
+  }
   if (N <= 32) return launch_c2r<1, OT>(spec, y, tab, e, B, Co, RPI, N, P, Kd, npad, st);
   if (N <= 64) return launch_c2r<2, OT>(spec, y, tab, e, B, Co, RPI, N, P, Kd, npad, st);
   if (N <= 96) return launch_c2r<3, OT>(spec, y, tab, e, B, Co, RPI, N, P, Kd, npad, st);

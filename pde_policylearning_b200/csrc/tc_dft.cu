@@ -181,7 +181,8 @@ k_fwd_tc(const __grid_constant__ CUtensorMap tmx, const FdTc p) {
 #pragma unroll
             for (int j = 0; j < 4; j++) mma_tf32_ts(d, xa + 32 + 8 * j, dt + (uint64_t)(j * 16), idesc, 1u);
           } else {
-            for (int pass = 0; pass < ((p.debug & 2) ? 0 : p.npass); pass++) {
+            _Pragma("unroll") for (int pass = 0; pass < 3; pass++) {
+              if (pass >= ((p.debug & 2) ? 0 : p.npass)) break;
               const uint32_t ac = pass == 1 ? xa + 32 : xa;
               const uint64_t dt = (pass == 2 ? d_tl : d_th) + (uint64_t)(c * 64);     // 32 K elements = 8 chunks of 128 B
 #pragma unroll
@@ -212,7 +213,8 @@ k_fwd_tc(const __grid_constant__ CUtensorMap tmx, const FdTc p) {
             for (int j = 0; j < H / 8; j++)
               mma_tf32_ts(d, t_mt + H + 8 * j, db2 + (uint64_t)(j * (2 * kB2Lbo / 16)), idesc, 1u);
           } else {
-            for (int pass = 0; pass < p.npass; pass++) {
+            _Pragma("unroll") for (int pass = 0; pass < 3; pass++) {
+            if (pass >= p.npass) break;   // compile-time trip count (descriptors stay folded); 1-pass mode leaves early
               const uint32_t am = pass == 1 ? t_mt + H : t_mt;
               const uint32_t bb = (pass == 2 ? bl : bh) + (uint32_t)(r * H / 4) * kB2Lbo;
               const uint64_t db2 = smem_desc(bb, kB2Lbo, kB2Sbo, LAYOUT_NONE);

@@ -149,7 +149,8 @@ k_mix_tc(const MixTc p) {
       if (warp == 0) {
         if (elect_one()) {
           uint32_t acc = 0;
-          for (int pass = 0; pass < p.npass; pass++) {
+          _Pragma("unroll") for (int pass = 0; pass < 3; pass++) {
+            if (pass >= p.npass) break;   // compile-time trip count (descriptors stay folded); 1-pass mode leaves early
             const uint32_t a = pass == 1 ? t_al : t_ah;
             const uint64_t db = pass == 2 ? d_bl : d_bh;
             for (int ks = 0; ks < Kp / 8; ks++) {
@@ -298,7 +299,8 @@ k_dw_tc(const DwTc p) {
       __syncthreads();
       if (warp == 0) {
         if (elect_one()) {
-          for (int pass = 0; pass < p.npass; pass++) {
+          _Pragma("unroll") for (int pass = 0; pass < 3; pass++) {
+            if (pass >= p.npass) break;   // compile-time trip count (descriptors stay folded); 1-pass mode leaves early
             const uint32_t aoff = pass == 1 ? abytes : 0u;                       // A: hi, lo, hi
             const uint32_t boff = 2 * abytes + (pass == 2 ? bbytes : 0u);        // B: hi, hi, lo
             const uint64_t da = smem_desc(sbase + aoff, kDwLbo, kDwSbo, LAYOUT_NONE);

@@ -169,7 +169,8 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
         const uint32_t d = t_acc1 + 64u * ab;
         const uint64_t woff = (uint64_t)((uint32_t)c * 8u * sbo1 / 16u);   // 64 rows = 8 row groups
         uint32_t acc = 0;
-        for (int pass = 0; pass < p.npass; pass++) {
+        _Pragma("unroll") for (int pass = 0; pass < 3; pass++) {
+            if (pass >= p.npass) break;   // compile-time trip count (descriptors stay folded); 1-pass mode leaves early
           const uint32_t ac = pass == 1 ? t_x + p.Cip : t_x;
           const uint64_t dw = (pass == 2 ? d_w1l : d_w1h) + woff;
           for (int k = 0; k < k1; k++) { mma_tf32_ts(d, ac + 8 * k, dw + (uint64_t)(k * 16), id1, acc); acc = 1; }
@@ -201,7 +202,8 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
           const uint32_t d = t_acc2 + (uint32_t)(it & 1) * p.N2;
           const uint32_t fa = t_f + 128u * fb;
           const uint64_t koff = (uint64_t)(c * 16 * 8);   // 64 k = 16 chunks of 4, 128 B each -> /16
-          for (int pass = 0; pass < p.npass; pass++) {
+          _Pragma("unroll") for (int pass = 0; pass < 3; pass++) {
+            if (pass >= p.npass) break;   // compile-time trip count (descriptors stay folded); 1-pass mode leaves early
             const uint32_t ac = pass == 1 ? fa + 64 : fa;
             const uint64_t dw = (pass == 2 ? d_w2l : d_w2h) + koff;
             for (int k = 0; k < 8; k++) mma_tf32_ts(d, ac + 8 * k, dw + (uint64_t)(k * 16), id2, (c > 0 || pass > 0 || k > 0) ? 1u : 0u);

@@ -212,7 +212,8 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
         const uint32_t xa = a_base + (uint32_t)xi * a_width;
         uint32_t acc = 0;
         if (!nomma && elect_one()) {
-          for (int pass = 0; pass < p.npass; pass++) {
+          _Pragma("unroll") for (int pass = 0; pass < 3; pass++) {
+            if (pass >= p.npass) break;   // compile-time trip count (descriptors stay folded); 1-pass mode leaves early
             const uint32_t ac = pass == 1 ? xa + p.C1p : xa;
             const uint64_t dw = pass == 2 ? d_w1l : d_w1h;
             for (int k = 0; k < p.C1p / 8; k++) {
@@ -222,7 +223,8 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
           }
           if (p.C2p) {
             const uint32_t x2 = xa + 2 * p.C1p;
-            for (int pass = 0; pass < p.npass; pass++) {
+            _Pragma("unroll") for (int pass = 0; pass < 3; pass++) {
+            if (pass >= p.npass) break;   // compile-time trip count (descriptors stay folded); 1-pass mode leaves early
               const uint32_t ac = pass == 1 ? x2 + p.C2p : x2;
               const uint64_t dw = pass == 2 ? d_w2l : d_w2h;
               for (int k = 0; k < p.C2p / 8; k++) mma_tf32_ts(d, ac + 8 * k, dw + (uint64_t)(k * 16), idesc, 1);
@@ -232,7 +234,8 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
             // B operand A'[n = channel][k = (row, q)]: K-chunks outermost (LBO = Np/8 * 128), channel groups 128 B apart
             const uint64_t d_ah = smem_desc(st + L.ah, lbo_a, 128, LAYOUT_NONE);
             const uint64_t d_al = smem_desc(st + L.al, lbo_a, 128, LAYOUT_NONE);
-            for (int pass = 0; pass < p.npass; pass++) {
+            _Pragma("unroll") for (int pass = 0; pass < 3; pass++) {
+            if (pass >= p.npass) break;   // compile-time trip count (descriptors stay folded); 1-pass mode leaves early
               const uint32_t tcn = pass == 1 ? t_lo : t_hi;
               const uint64_t da = pass == 2 ? d_al : d_ah;
               for (int k = 0; k < p.Ks / 8; k++)

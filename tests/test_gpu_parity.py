@@ -898,7 +898,8 @@ def test_single_pass_tf32_mode_within_2e2():
     assert errs["tf32"] > 3 * errs["fp32"]
 
 
-def test_3d_layer_pointwise_on_tensor_cores():
+@pytest.mark.parametrize("m", [(3, 3, 4), (3, 2, 8)], ids=str)
+def test_3d_layer_pointwise_on_tensor_cores(m):
     """PINO layer shape class (3-D, rows that are not multiples of the pixel tile): spectral conv + Conv1d(k=1) + bias +
     GELU with the 1x1 convolution on the tcgen05 tile kernel (transform result handed over through `add`), y, dx and
     parameter gradients vs the float64 closed form; the tile kernel must actually run."""
@@ -907,7 +908,8 @@ def test_3d_layer_pointwise_on_tensor_cores():
     from pde_policylearning_b200 import ops
     dev = _dev()
     torch.manual_seed(6)
-    B, C, grid, m = 2, 16, (8, 8, 18), (3, 3, 4)          # 8 * 8 * 18 = 1152 = 9 * 128 pixels, rows of 18
+    B, C, grid = 2, 16, (8, 8, 18)                         # 8 * 8 * 18 = 1152 = 9 * 128 pixels, rows of 18; 8 kept last-dim
+                                                           # modes take the k_c2r_plain8 / k_r2c_rows kernels of the PINO shape
     conv = P.PinoSpectralConv3d(C, C, *m)
     w = torch.randn(C, C, 1) * 0.3
     bias = torch.randn(C)
