@@ -135,6 +135,82 @@ k_r2c_rows(const float* __restrict__ x, float* __restrict__ out, const float* __
   }
 }
 
+// 32 rows per warp, lane = row: the table row of a sample is read with warp-UNIFORM vector loads (one shared-memory
+// wavefront each, whatever the number of lanes), so a sample costs Q2P / 4 + 1 wavefronts for 32 x Q2P FMAs -- the 8-row
+// variant above pays 5 wavefronts for 8 x 16 and was LSU-bound (214 us for the 306 MB PINO pass).
+template <int Q2P>
+__global__ void __launch_bounds__(256)
+k_r2c_rows32(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ tab, long R, int N, int npad, int q2) {
+  extern __shared__ float s_dyn[];
+  const int NS = N | 1;                               // odd row stride: lane-strided reads are conflict-free
+  float* s_tabT = s_dyn;                              // [N][Q2P]
+  float* s_rows = s_dyn + (size_t)N * Q2P;            // [8 warps][32 NS]
+  for (int i = threadIdx.x; i < N * Q2P; i += 256) {
+    const int n = i / Q2P, q = i - n * Q2P;
+    s_tabT[i] = q < q2 ? tab[(size_t)q * npad + n] : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* rows = s_rows + (size_t)warp * 32 * NS;
+  const long ngroups = R >> 5;                        // R % 32 == 0 (checked by the launcher)
+  for (long g = (long)blockIdx.x * 8 + warp; g < ngroups; g += (long)gridDim.x * 8) {
+    const float* src = x + (g << 5) * N;
+    if (NS == N) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      for (int i = lane; i < 8 * N; i += 32) reinterpret_cast<float4*>(rows)[i] = __ldg(s4 + i);
+    } else {
+      for (int i = lane; i < 32 * N; i += 32) {
+        const int rr = i / N, n = i - rr * N;
+        rows[rr * NS + n] = __ldg(src + i);
+      }
+    }
+    __syncwarp();
+    float acc[Q2P];
+#pragma unroll
+    for (int i = 0; i < Q2P; i++) acc[i] = 0.f;
+    const float* xr = rows + lane * NS;
+#pragma unroll 2
+    for (int n = 0; n < N; n++) {
+      const float xv = xr[n];
+      const float4* t4 = reinterpret_cast<const float4*>(s_tabT + n * Q2P);
+#pragma unroll
+      for (int i = 0; i < Q2P / 4; i++) {
+        const float4 t = t4[i];
+        acc[4 * i] = fmaf(xv, t.x, acc[4 * i]);
+        acc[4 * i + 1] = fmaf(xv, t.y, acc[4 * i + 1]);
+        acc[4 * i + 2] = fmaf(xv, t.z, acc[4 * i + 2]);
+        acc[4 * i + 3] = fmaf(xv, t.w, acc[4 * i + 3]);
+      }
+    }
+    float* dst = out + ((g << 5) + lane) * q2;
+    if (q2 == Q2P) {
+#pragma unroll
+      for (int i = 0; i < Q2P / 4; i++)
+        reinterpret_cast<float4*>(dst)[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < Q2P; i++)
+        if (i < q2) dst[i] = acc[i];
+    }
+    __syncwarp();
+  }
+}
+
+template <int Q2P>
+static int launch_r2c_rows32(const float* x, float* out, const float* tab, long R, int N, int npad, int q2, cudaStream_t st) {
+  const size_t smem = ((size_t)N * Q2P + (size_t)8 * 32 * (N | 1)) * sizeof(float);
+  if (smem > 48 * 1024)
+    B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_r2c_rows32<Q2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long ngroups = R / 32;
+  long blocks = (ngroups + 7) / 8;
+  const long cap = (long)b2no_sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_r2c_rows32<Q2P><<<(unsigned)blocks, 256, smem, st>>>(x, out, tab, R, N, npad, q2);
+  B2NO_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int QL>
 static int launch_r2c_rows(const float* x, float* out, const float* tab, long R, int N, int npad, int q2, cudaStream_t st) {
   const size_t smem = ((size_t)N * 4 * QL + (size_t)8 * 8 * N) * sizeof(float);
@@ -155,6 +231,12 @@ static int run_r2c(const b2no_plan* p, int which, const float* x, float* out, lo
   const int N = which == 0 ? p->g.nin[d - 1] : p->g.nout[d - 1];
   const int npad = which == 0 ? p->npad_in : p->npad_out;
   const float* tab = which == 0 ? p->t_in : p->t_out;
+  if (R % 32 == 0 && R >= 32 * 8 * 64 && p->q2 <= 16 && p->q2 % 4 == 0 && N >= 8 && N <= 160 && (((uintptr_t)x) & 15) == 0 &&
+      (((uintptr_t)out) & 15) == 0) {
+    // many rows: lane = row (warp-uniform table reads)
+    if (p->q2 <= 8) return launch_r2c_rows32<8>(x, out, tab, R, N, npad, p->q2, st);
+    return launch_r2c_rows32<16>(x, out, tab, R, N, npad, p->q2, st);
+  }
   if (R % 8 == 0 && p->q2 <= 16 && N >= 8 && N <= 512 && (((uintptr_t)x) & 15) == 0) {
     if (p->q2 <= 4) return launch_r2c_rows<1>(x, out, tab, R, N, npad, p->q2, st);
     if (p->q2 <= 8) return launch_r2c_rows<2>(x, out, tab, R, N, npad, p->q2, st);

@@ -908,8 +908,10 @@ def test_3d_layer_pointwise_on_tensor_cores(m):
     from pde_policylearning_b200 import ops
     dev = _dev()
     torch.manual_seed(6)
-    B, C, grid = 2, 16, (8, 8, 18)                         # 8 * 8 * 18 = 1152 = 9 * 128 pixels, rows of 18; 8 kept last-dim
-                                                           # modes take the k_c2r_plain8 / k_r2c_rows kernels of the PINO shape
+    # 8 * 8 * 18 = 1152 = 9 * 128 pixels, rows of 18.  The second case (8 kept last-dim modes, 32768 rows) takes the kernels
+    # of the PINO shape: k_r2c_rows32 (lane = row) and k_c2r_plain8
+    B, C = 2, 16
+    grid = (8, 8, 18) if m[2] != 8 else (32, 32, 18)
     conv = P.PinoSpectralConv3d(C, C, *m)
     w = torch.randn(C, C, 1) * 0.3
     bias = torch.randn(C)
