@@ -560,6 +560,41 @@ k_dw(const float2* __restrict__ xh, const float2* __restrict__ gyh, b2no_weights
       }
 }
 
+// Small batches (PINO: B = 4, 2048 modes, 64 x 64 channels -> 67 MB of dW per layer): the output is the traffic.  One block
+// per (256 modes, input channel i); a thread decodes its mode ONCE, keeps conj(Xh[b, i, k]) in registers and walks the
+// output channels, so every dW element costs BT loads (L2-resident gYh) + one coalesced store instead of a mode decode
+// (eight integer divisions) per element as in k_dw2.
+template <int BT>
+__global__ void __launch_bounds__(256)
+k_dw_small(const float2* __restrict__ xh, const float2* __restrict__ gyh, b2no_weights w, ModeMap mm, int B, int Ci, int Co,
+           int Kt, int accumulate) {
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  const int i = blockIdx.y;
+  if (k >= Kt) return;
+  int corner;
+  long woff;
+  decode_mode(mm, w, k, &corner, &woff);
+  float2 xv[BT];
+#pragma unroll
+  for (int b = 0; b < BT; b++) xv[b] = b < B ? __ldg(xh + ((size_t)b * Ci + i) * Kt + k) : make_float2(0.f, 0.f);
+  float2* dst = (float2*)w.corner[corner] + woff + (long)i * w.stride_i;
+  const float2* gp = gyh + k;
+  for (int o = 0; o < Co; o++) {
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int b = 0; b < BT; b++) {
+      if (b < B) {
+        const float2 gv = __ldg(gp + ((size_t)b * Co + o) * Kt);
+        acc.x = fmaf(xv[b].x, gv.x, fmaf(xv[b].y, gv.y, acc.x));
+        acc.y = fmaf(xv[b].x, gv.y, fmaf(-xv[b].y, gv.x, acc.y));
+      }
+    }
+    float2* d = dst + (long)o * w.stride_o;
+    if (accumulate) { const float2 old = *d; acc.x += old.x; acc.y += old.y; }
+    *d = acc;
+  }
+}
+
 extern "C" int b2no_mix_dw(const b2no_plan* p, const float* xh, const float* gyh, const b2no_weights* dw,
                            int batch, int ci, int co, int accumulate, void* stream) {
   if (!p || !xh || !gyh || !dw || batch < 1 || ci < 1 || co < 1) return B2NO_E_ARG;
@@ -569,6 +604,15 @@ extern "C" int b2no_mix_dw(const b2no_plan* p, const float* xh, const float* gyh
   {
     const int rc = b2no_tc_mix_dw(p, xh, gyh, dw, batch, ci, co, accumulate, st);
     if (rc != 1) return rc;
+  }
+  if (batch <= 8 && Kt >= 256) {
+    dim3 grid((unsigned)((Kt + 255) / 256), (unsigned)ci);
+    if (batch <= 4)
+      k_dw_small<4><<<grid, 256, 0, st>>>((const float2*)xh, (const float2*)gyh, *dw, mm, batch, ci, co, Kt, accumulate);
+    else
+      k_dw_small<8><<<grid, 256, 0, st>>>((const float2*)xh, (const float2*)gyh, *dw, mm, batch, ci, co, Kt, accumulate);
+    B2NO_LAUNCH_CHECK();
+    return 0;
   }
   const long total = (long)ci * co * Kt;
   k_dw2<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float2*)xh, (const float2*)gyh, *dw, mm, batch, ci, co, Kt, accumulate);
