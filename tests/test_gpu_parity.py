@@ -250,11 +250,16 @@ def _run_model(mod, c, dev, loss_fn=None, tol=TOL, gtol=5e-5):
     assert abs(loss.item() - c["loss"].item()) <= 2e-5 * abs(c["loss"].item()), "loss"
     names = [n for n, _ in mod.named_parameters()]
     gs = torch.autograd.grad(loss, [p for _, p in mod.named_parameters()], allow_unused=True)
-    worst = 0.0
+    worst, where = 0.0, ""
     for n, g in zip(names, gs):
         assert g is not None, f"{n} got no gradient"   # test_tfno.py:61-65: every parameter is reached
-        worst = max(worst, rel(g, c["grads"][n]))
-        assert rel(g, c["grads"][n]) < gtol, n
+        e = rel(g, c["grads"][n])
+        if e > worst:
+            worst, where = e, n
+        assert e < gtol, (n, e)
+    # the margin against the tolerance is part of the record (pytest -s / the per-test logs under gpurun_out/)
+    print(f"[{type(mod).__name__}] output {rel(out, c['out']):.2e} (tol {tol:.0e}), worst parameter gradient {worst:.2e} at {where} "
+          f"(tol {gtol:.0e})")
     return worst
 
 
