@@ -831,8 +831,20 @@ def _pino_trunk_forward(x, re, fc0, mnet1, sp_convs, ws, mnet2, fc1, fc2, act_na
     h = Fn.pointwise_conv(x6.contiguous(), w6, None, None)
     # ---- Fourier layers ----
     L = len(ws)
-    for i, (conv, w) in enumerate(zip(sp_convs, ws)):
-        h = conv.forward_fused(h, bias=w.bias, pw_weight=w.weight, act=act_name if i != L - 1 else None)
+    same = all((c.in_channels, c.out_channels, c.modes1, c.modes2, c.modes3) ==
+               (sp_convs[0].in_channels, sp_convs[0].out_channels, sp_convs[0].modes1, sp_convs[0].modes2, sp_convs[0].modes3)
+               for c in sp_convs) and sp_convs[0].in_channels == sp_convs[0].out_channels
+    if same and L > 1:
+        # equal layers (the yaml configuration): the whole stack as ONE autograd node -- its backward chains act'(z) of the
+        # layer below into each dx pass (no separate activation-backward pass over the activations)
+        geom = sp_convs[0].geom(tuple(h.shape[2:]))
+        bias_all = torch.stack([w.bias for w in ws], dim=0)
+        layers = [(w.weight, conv.corners()) for conv, w in zip(sp_convs, ws)]
+        acts = [act_name if i != L - 1 else None for i in range(L)]
+        h = Fn.fno_stack(h, geom, bias_all, layers, acts)
+    else:
+        for i, (conv, w) in enumerate(zip(sp_convs, ws)):
+            h = conv.forward_fused(h, bias=w.bias, pw_weight=w.weight, act=act_name if i != L - 1 else None)
     # ---- tail: fold MultiplicativeNet2 into fc1; run on the padded grid, slice the result ----
     w1 = fc1.weight @ mnet2.B                                     # (fc_dim, C)
     wre = fc1.weight @ mnet2.A                                    # (fc_dim, 1)
