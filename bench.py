@@ -311,7 +311,8 @@ def bench_cfg3(dev, rank, world, timed, steps=3, warmup=2, B=None, T=None, graph
     model = P.RNO2dObserver(12, 12, 34, 0, layer_num=1).to(dev).eval()
     x = _grf((B, T), 32, 300 + rank, dev).unsqueeze(-1)
     tgt = _grf((B,), 32, 400 + rank, dev).unsqueeze(-1)
-    opt = P.FusedAdam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    overlap = os.environ.get("B2NO_OVERLAP_AR", "0") not in ("", "0") and world > 1
+    opt = P.FusedAdam(model.parameters(), lr=1e-3, weight_decay=1e-4, overlap_allreduce=overlap)
     lf = lambda o, t: P.rel_l2_loss(o.reshape(B, -1), t.reshape(B, -1), size_average=False)
 
     def eager():
@@ -368,7 +369,8 @@ def bench_cfg4(dev, rank, world, timed, steps=5, warmup=3, B=None):
     u = (a0.unsqueeze(-1) * torch.cos(gt * 3.0).reshape(1, 1, 1, T)).contiguous()
     re = (torch.randint(100, 501, (B,), generator=torch.Generator().manual_seed(600 + rank)).float()).to(dev)
     forcing = P.get_forcing(S, device=dev)
-    opt = P.FusedAdam(model.parameters(), lr=1e-3)
+    overlap = os.environ.get("B2NO_OVERLAP_AR", "0") not in ("", "0") and world > 1
+    opt = P.FusedAdam(model.parameters(), lr=1e-3, overlap_allreduce=overlap)
 
     def step():
         opt.zero_grad(set_to_none=True)
@@ -504,7 +506,9 @@ def run_b200(args):
     model = P.FNO2dObserver(MODES, MODES, WIDTH).to(dev)
     lp = P.LpLoss(size_average=False)
     loss_fn = lambda out, tgt: lp(out, tgt)
-    opt = P.FusedAdam(model.parameters(), lr=1e-3, weight_decay=1e-4)   # run_pde_observers.py:134
+    overlap = os.environ.get("B2NO_OVERLAP_AR", "0") not in ("", "0") and world > 1
+    opt = P.FusedAdam(model.parameters(), lr=1e-3, weight_decay=1e-4, overlap_allreduce=overlap,   # run_pde_observers.py:134
+                      bucket_bytes=int(os.environ.get("B2NO_BUCKET_BYTES", str(1 << 20))))
     p_host = synthetic_fields(BATCH, GRID, seed=100 + rank).pin_memory()
     t_host = synthetic_fields(BATCH, GRID, seed=200 + rank).permute(0, 3, 1, 2).contiguous().pin_memory()
     p_dev, t_dev = p_host.to(dev), t_host.to(dev)
@@ -619,6 +623,9 @@ def run_b200(args):
         cfg = config_dict(world)
         cfg["cuda_graph"] = graphed is not None
         cfg["optimizer"] = "fused flat Adam (lr 1e-3, weight_decay 1e-4), inside the timed step"
+        cfg["grad_allreduce"] = ("none (1 GPU)" if world == 1 else
+                                 ("per-bucket NCCL all-reduce launched from gradient hooks during backward (B2NO_OVERLAP_AR=1)"
+                                  if overlap else "one NCCL all-reduce of the flat bucket after backward"))
         out = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
