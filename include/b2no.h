@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define B2NO_MAX_DIM 3
-#define B2NO_ABI_VERSION 3
+#define B2NO_ABI_VERSION 4
 
 enum { B2NO_NORM_BACKWARD = 0, B2NO_NORM_FORWARD = 1, B2NO_NORM_ORTHO = 2 };
 enum { B2NO_ACT_NONE = 0, B2NO_ACT_GELU = 1, B2NO_ACT_RELU = 2, B2NO_ACT_SIGMOID = 3, B2NO_ACT_SELU = 4,
@@ -55,6 +55,12 @@ typedef struct {
   int32_t nout[B2NO_MAX_DIM];
   int32_t half[B2NO_MAX_DIM];
   int32_t norm;
+  /* layout of the kept-mode spectra this plan's transforms write / read and its mixing calls work on:
+   *   0  (batch, channel, K_1..K_d)   the default (what a reader of rfftn's output would expect)
+   *   1  (K_1..K_d, batch, channel)   mode-major: the per-mode [batch x channel] slab of the mixing GEMMs is contiguous.
+   *      2-D plans on the tensor-core transform kernels only (b2no_plan_layout_supported); used by the RNO layer, where
+   *      the mixing is real tensor-core work (rno.py:51-58,71-74 at batch 256) */
+  int32_t spec_layout;
 } b2no_geom;
 
 typedef struct b2no_plan b2no_plan;
@@ -104,6 +110,8 @@ int b2no_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_by
 /* ---- plans ------------------------------------------------------------------------------------- */
 int b2no_plan_create(const b2no_geom* geom, b2no_plan** out);
 int b2no_plan_destroy(b2no_plan* plan);
+/* 1 when every transform / mixing call of this plan can run with its spec_layout for (batch, channels) tensors */
+int b2no_plan_layout_supported(const b2no_plan* plan, int64_t batch, int64_t channels);
 /* kept modes per dim (K_j) */
 int b2no_plan_kept(const b2no_plan* plan, int32_t kept[B2NO_MAX_DIM]);
 /* floats of scratch needed by dft_forward / dft_inverse for a (batch, channels) tensor */

@@ -21,7 +21,8 @@ ACT = {None: 0, "none": 0, "identity": 0, "gelu": 1, "relu": 2, "sigmoid": 3, "s
 
 class Geom(C.Structure):
     _fields_ = [("ndim", C.c_int32), ("nin", C.c_int32 * MAX_DIM), ("nfft", C.c_int32 * MAX_DIM),
-                ("nout", C.c_int32 * MAX_DIM), ("half", C.c_int32 * MAX_DIM), ("norm", C.c_int32)]
+                ("nout", C.c_int32 * MAX_DIM), ("half", C.c_int32 * MAX_DIM), ("norm", C.c_int32),
+                ("spec_layout", C.c_int32)]
 
 
 class Weights(C.Structure):
@@ -99,6 +100,7 @@ def lib():
     L.b2no_plan_create.argtypes = [C.POINTER(Geom), C.POINTER(vp)]
     L.b2no_plan_destroy.argtypes = [vp]
     L.b2no_plan_kept.argtypes = [vp, C.POINTER(C.c_int32 * MAX_DIM)]
+    L.b2no_plan_layout_supported.argtypes = [vp, i64, i64]
     L.b2no_plan_workspace_floats.restype = i64
     L.b2no_plan_workspace_floats.argtypes = [vp, i64, i64]
     L.b2no_set_tensor_core_mode.argtypes = [i32]
@@ -142,7 +144,7 @@ def lib():
 
 EXPORTS = [
     "b2no_version", "b2no_error_string", "b2no_device_info",
-    "b2no_plan_create", "b2no_plan_destroy", "b2no_plan_kept", "b2no_plan_workspace_floats",
+    "b2no_plan_create", "b2no_plan_destroy", "b2no_plan_kept", "b2no_plan_layout_supported", "b2no_plan_workspace_floats",
     "b2no_set_tensor_core_mode", "b2no_set_precision", "b2no_tensor_core_launches", "b2no_kernel_launches",
     "b2no_dft_forward", "b2no_dft_inverse", "b2no_mix", "b2no_mix_dw",
     "b2no_act_bwd", "b2no_pw_wgrad_scratch_floats", "b2no_pw_wgrad", "b2no_mlp_head_fwd", "b2no_mlp_head_bwd_scratch_floats", "b2no_mlp_head_bwd_supported", "b2no_mlp_head_bwd",

@@ -121,6 +121,8 @@ static inline int total_modes(const b2no_plan* p) {
 }
 
 // tensor-core per-mode mixing (tc_mix.cu): return 0 = ran, 1 = shape not eligible (caller uses the CUDA-core kernel)
+int b2no_tc_mix_feasible(int batch, int ci, int co, int mode);
+int b2no_tc_mix_dw_feasible(int batch, int ci, int co);
 int b2no_tc_mix(const b2no_plan* p, int mode, const float* in, const b2no_weights* w, float* out, int batch, int ci, int co,
                 int accumulate, cudaStream_t st);
 int b2no_tc_mix_dw(const b2no_plan* p, const float* xh, const float* gyh, const b2no_weights* dw, int batch, int ci, int co,

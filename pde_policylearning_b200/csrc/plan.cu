@@ -117,6 +117,8 @@ extern "C" int b2no_plan_create(const b2no_geom* g, b2no_plan** out) {
     if (j < d - 1 && g->half[j] > g->nfft[j]) return B2NO_E_ARG;
   }
   if (g->norm < 0 || g->norm > 2) return B2NO_E_ARG;
+  if (g->spec_layout != 0 && g->spec_layout != 1) return B2NO_E_ARG;
+  if (g->spec_layout == 1 && d != 2) return B2NO_E_UNSUPPORTED;
 
   b2no_plan* p = (b2no_plan*)calloc(1, sizeof(b2no_plan));
   if (!p) return B2NO_E_ARG;

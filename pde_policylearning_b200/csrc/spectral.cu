@@ -333,6 +333,7 @@ extern "C" int b2no_dft_forward(const b2no_plan* p, int which, const float* x, f
     const int rc = b2no_tc_dft_forward(p, which, x, spec, (long)bc, st);
     if (rc != 1) return rc;
   }
+  if (p->g.spec_layout != 0) return B2NO_E_UNSUPPORTED;     // mode-major spectra exist on the tensor-core kernels only
   if (!work) return B2NO_E_ARG;
   float2* A = (float2*)work;
   if (d == 2) {
@@ -504,6 +505,7 @@ extern "C" int b2no_mix(const b2no_plan* p, int mode, const float* in, const b2n
     const int rc = b2no_tc_mix(p, mode, in, w, out, batch, ci, co, accumulate, st);
     if (rc != 1) return rc;
   }
+  if (p->g.spec_layout != 0) return B2NO_E_UNSUPPORTED;
   const int Cq = mode == 0 ? ci : co, Cp = mode == 0 ? co : ci;
   const long total = (long)batch * Cp * Kt;
   const unsigned blocks = (unsigned)((total + 255) / 256);
@@ -605,6 +607,7 @@ extern "C" int b2no_mix_dw(const b2no_plan* p, const float* xh, const float* gyh
     const int rc = b2no_tc_mix_dw(p, xh, gyh, dw, batch, ci, co, accumulate, st);
     if (rc != 1) return rc;
   }
+  if (p->g.spec_layout != 0) return B2NO_E_UNSUPPORTED;
   if (batch <= 8 && Kt >= 256) {
     dim3 grid((unsigned)((Kt + 255) / 256), (unsigned)ci);
     if (batch <= 4)
@@ -918,6 +921,22 @@ static int run_c2r(const float2* spec, float* y, const float* tab, const EpiDev&
   return launch_c2r<4, OT>(spec, y, tab, e, B, Co, RPI, N, P, Kd, npad, st);
 }
 
+// Mode-major spectra (b2no_geom.spec_layout = 1) live on the tensor-core kernels only: every call the RNO layer makes with
+// base width `channels` (mixing C -> C, C -> 2C, 2C -> C and their weight gradients, transforms of C and 2C channel tensors)
+// must be eligible, otherwise the caller keeps the default layout.
+extern "C" int b2no_plan_layout_supported(const b2no_plan* p, int64_t batch, int64_t channels) {
+  if (!p || batch < 1 || channels < 1) return 0;
+  if (p->g.spec_layout == 0) return 1;
+  if (!b2no_tc_available() || p->g.ndim != 2) return 0;
+  if (!p->tcf[0].tb || !p->tcf[1].tb || !p->tc[0].timg || !p->tc[1].timg) return 0;
+  if (((long)p->g.nin[0] * p->g.nin[1]) % 128 != 0 || ((long)p->g.nout[0] * p->g.nout[1]) % 128 != 0) return 0;
+  if (p->K[0] > 32) return 0;
+  if (((size_t)2 * channels * ((size_t)p->K[0] * p->K[1] + 1) + (size_t)p->K[0] * 32) * 8 > 200 * 1024) return 0;   // k_inv_h staging
+  const int c = (int)channels, b = (int)(batch > 1 << 30 ? 1 << 30 : batch);
+  return b2no_tc_mix_feasible(b, c, c, 0) && b2no_tc_mix_feasible(b, c, 2 * c, 0) && b2no_tc_mix_feasible(b, c, 2 * c, 1) &&
+         b2no_tc_mix_dw_feasible(b, c, c) && b2no_tc_mix_dw_feasible(b, c, 2 * c);
+}
+
 // n x n identity matrices on the device, one per (device, n), created on first use (never inside a graph capture: the
 // first call of every shape is an eager warm-up, as for the plans) and kept for the life of the process
 __global__ void k_fill_identity(float* m, int n) {
@@ -966,6 +985,7 @@ extern "C" int b2no_dft_inverse(const b2no_plan* p, int which, const float* spec
     const int rc = b2no_tc_pointwise(p, which, spec, y, work, batch, channels, px, epi, st);
     if (rc != 1) return rc;
   }
+  if (spec && p && p->g.spec_layout != 0) return B2NO_E_UNSUPPORTED;
   auto set_strides = [&](long P_) {
     e.mul_bs = (epi && epi->mul_bstride) ? (long)epi->mul_bstride : (long)channels * P_;
     e.gate_bs = (epi && epi->gate_bstride) ? (long)epi->gate_bstride : (long)channels * P_;

@@ -41,6 +41,7 @@ struct FdTc {
   float* spec;
   int debug;   // ablation switches (B2NO_FD_DEBUG): 1 no converter TMEM stores, 2 no MMAs, 4 no hand-over stores, 8 no lo split
   int npass;   // 3: 3xTF32, 1: single-pass TF32 (never merged)
+  int layout;  // 0: spectrum (plane, kx, ky); 1: mode-major (kx, ky, plane)
 };
 
 struct FdLayout { uint32_t tbh, tbl, b2, b2_bytes, xch, mts, mts_stride, stages, bars, total; };
@@ -396,10 +397,19 @@ k_fwd_tc(const __grid_constant__ CUtensorMap tmx, const FdTc p) {
           const long plane = tile * R + r;
           if (lane < Kx && plane < p.planes) {
             const float* im = xch + ((size_t)r * 32 + lane) * N1;
-            float2* dst = (float2*)p.spec + ((size_t)plane * Kx + lane) * Ky;
+            if (p.layout == 0) {
+              float2* dst = (float2*)p.spec + ((size_t)plane * Kx + lane) * Ky;
 #pragma unroll
-            for (int ky = 0; ky < 16; ky++)
-              if (ky < Ky) dst[ky] = make_float2(v[2 * ky] - im[2 * ky + 1], v[2 * ky + 1] + im[2 * ky]);
+              for (int ky = 0; ky < 16; ky++)
+                if (ky < Ky) dst[ky] = make_float2(v[2 * ky] - im[2 * ky + 1], v[2 * ky + 1] + im[2 * ky]);
+            } else {
+              // mode-major: the R planes of a tile are consecutive channels of one sample, so the R stores of a mode fall
+              // into one or two 32-byte sectors (merged in L2); same number of store instructions as the default layout
+              float2* dst = (float2*)p.spec + (size_t)lane * Ky * p.planes + plane;
+#pragma unroll
+              for (int ky = 0; ky < 16; ky++)
+                if (ky < Ky) dst[(size_t)ky * p.planes] = make_float2(v[2 * ky] - im[2 * ky + 1], v[2 * ky + 1] + im[2 * ky]);
+            }
           }
         }
         tc_fence_before();
@@ -434,7 +444,7 @@ int b2no_tc_dft_forward(const b2no_plan* plan, int which, const float* x, float*
   p.planes = planes;
   const long rows = planes * tf.H;
   p.tiles = (rows + 127) / 128;
-  p.tb = tf.tb; p.mimg = tf.mimg; p.spec = spec;
+  p.tb = tf.tb; p.mimg = tf.mimg; p.spec = spec; p.layout = plan->g.spec_layout;
   B2NO_ENV_ONCE(env_debug, "B2NO_FD_DEBUG", 0);
   B2NO_ENV_ONCE(env_merge, "B2NO_FD_MERGE", 1);
   p.debug = env_debug;

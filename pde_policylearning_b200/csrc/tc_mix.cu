@@ -37,6 +37,7 @@ constexpr int kMixThreads = 256;
 
 struct MixTc {
   int B, Cq, Cp, Kt, Kp, Np, conjt, accumulate, npass;
+  int layout;        // spectra: 0 (batch, channel, mode), 1 (mode, batch, channel)
   const float2* in;
   float2* out;
   b2no_weights w;
@@ -117,16 +118,33 @@ k_mix_tc(const MixTc p) {
       // ---- A operand: this lane's sample, all contraction channels of mode k -> TMEM (hi | lo); the two warps of a
       //      quadrant take alternate 8-channel chunks; up to three chunks (24 gathers) are in flight per thread ----
       {
-        const float2* src = p.in + ((size_t)(b < p.B ? b : 0) * p.Cq) * p.Kt + k;
+        const int bb = b < p.B ? b : 0;
+        // layout 0: channel stride Kt (8-byte gathers, one 32-byte sector each); layout 1: the sample's Cq values of this
+        // mode are contiguous (the sectors a thread touches are fully used, by itself, a few loads later)
+        const float2* src = p.layout ? p.in + ((size_t)k * p.B + bb) * p.Cq : p.in + ((size_t)bb * p.Cq) * p.Kt + k;
+        const size_t cs = p.layout ? 1 : (size_t)p.Kt;
+        const bool vec = p.layout && !(p.Cq & 1);      // mode-major, even channel count: two channels per 16-byte load
         for (int cb = grp * 8; cb * 2 < Kp; cb += 48) {
           float2 v[3][8];
+          if (vec) {
 #pragma unroll
-          for (int u = 0; u < 3; u++)
+            for (int u = 0; u < 3; u++)
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-              const int c = cb + 16 * u + j;
-              v[u][j] = (b < p.B && c < p.Cq) ? __ldg(src + (size_t)c * p.Kt) : make_float2(0.f, 0.f);
-            }
+              for (int j = 0; j < 8; j += 2) {
+                const int c = cb + 16 * u + j;
+                const float4 t = (b < p.B && c < p.Cq) ? __ldg(reinterpret_cast<const float4*>(src + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[u][j] = make_float2(t.x, t.y);
+                v[u][j + 1] = make_float2(t.z, t.w);
+              }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 3; u++)
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                const int c = cb + 16 * u + j;
+                v[u][j] = (b < p.B && c < p.Cq) ? __ldg(src + (size_t)c * cs) : make_float2(0.f, 0.f);
+              }
+          }
 #pragma unroll
           for (int u = 0; u < 3; u++) {
             const int c0 = cb + 16 * u;
@@ -170,12 +188,24 @@ k_mix_tc(const MixTc p) {
         float v[8];
         tmem_ld8(t_d + lane_base + (uint32_t)c0, v);
         tmem_ld_wait();
-        if (b < p.B) {
+        if (b < p.B && p.layout && !(p.Cp & 1)) {
+          // mode-major, even channel count: the 4 outputs are two 16-byte stores into the sample's contiguous row
+#pragma unroll
+          for (int j = 0; j < 4; j += 2) {
+            const int o = (c0 >> 1) + j;
+            if (o < p.Cp) {
+              float4* dst = reinterpret_cast<float4*>(p.out + ((size_t)k * p.B + b) * p.Cp + o);
+              float4 r = make_float4(v[2 * j], v[2 * j + 1], v[2 * j + 2], v[2 * j + 3]);
+              if (p.accumulate) { const float4 old = *dst; r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w; }
+              *dst = r;
+            }
+          }
+        } else if (b < p.B) {
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             const int o = (c0 >> 1) + j;
             if (o < p.Cp) {
-              float2* dst = p.out + ((size_t)b * p.Cp + o) * p.Kt + k;
+              float2* dst = p.layout ? p.out + ((size_t)k * p.B + b) * p.Cp + o : p.out + ((size_t)b * p.Cp + o) * p.Kt + k;
               float2 r = make_float2(v[2 * j], v[2 * j + 1]);
               if (p.accumulate) { const float2 old = *dst; r.x += old.x; r.y += old.y; }
               *dst = r;
@@ -201,7 +231,7 @@ constexpr uint32_t kDwLbo = 144;                 // bytes between K-adjacent cor
 constexpr uint32_t kDwSbo = (kDwKB / 4) * kDwLbo;  // bytes between 8-row groups
 
 struct DwTc {
-  int B, Ci, Co, Kt, Np, Ga, accumulate, npass;      // Ga = 8-row groups of the A image that are materialised (2 Ci rows)
+  int B, Ci, Co, Kt, Np, Ga, accumulate, npass, layout;      // Ga = 8-row groups of the A image that are materialised (2 Ci rows)
   const float2* xh;
   const float2* gyh;
   b2no_weights w;
@@ -254,8 +284,10 @@ k_dw_tc(const DwTc p) {
     for (int ch = 0; ch < nchunks; ch++) {
       const int b = ch * kDwKB + bb;
       const bool live = b < p.B;
-      const float2* xs = p.xh + ((size_t)(live ? b : 0) * p.Ci) * p.Kt + k;
-      const float2* gs = p.gyh + ((size_t)(live ? b : 0) * p.Co) * p.Kt + k;
+      const int bl = live ? b : 0;
+      const float2* xs = p.layout ? p.xh + ((size_t)k * p.B + bl) * p.Ci : p.xh + ((size_t)bl * p.Ci) * p.Kt + k;
+      const float2* gs = p.layout ? p.gyh + ((size_t)k * p.B + bl) * p.Co : p.gyh + ((size_t)bl * p.Co) * p.Kt + k;
+      const size_t cs = p.layout ? 1 : (size_t)p.Kt;
       // the previous round of MMAs must have finished reading the operand images before they are overwritten
       if (pending) { mbar_wait(&bar, phase); phase ^= 1u; pending = false; }
       // gathers in batches of 8 (all in flight before the first shared-memory store)
@@ -264,7 +296,7 @@ k_dw_tc(const DwTc p) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
           const int i = i0 + u * nparts;
-          v[u] = (live && i < p.Ci) ? __ldg(xs + (size_t)i * p.Kt) : make_float2(0.f, 0.f);
+          v[u] = (live && i < p.Ci) ? __ldg(xs + (size_t)i * cs) : make_float2(0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < 8; u++) {
@@ -282,7 +314,7 @@ k_dw_tc(const DwTc p) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
           const int o = o0c + u * nparts;
-          v[u] = (live && o < p.Co) ? __ldg(gs + (size_t)o * p.Kt) : make_float2(0.f, 0.f);
+          v[u] = (live && o < p.Co) ? __ldg(gs + (size_t)o * cs) : make_float2(0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < 8; u++) {
@@ -361,11 +393,25 @@ int g_mix_min_batch = 96;    // below this a 128-sample tile is mostly padding: 
 
 }  // namespace
 
+// shape checks shared by the launchers and b2no_plan_layout_supported
+int b2no_tc_mix_feasible(int batch, int ci, int co, int mode) {
+  if (!b2no_tc_available() || batch < g_mix_min_batch) return 0;
+  const int Cq = mode == 0 ? ci : co, Cp = mode == 0 ? co : ci;
+  const int Kp = b2no_round_up(2 * Cq, 16), Np = b2no_round_up(2 * Cp, 16);
+  if (Np > 256 || 2 * Kp + Np > 512) return 0;
+  return 2 * (size_t)Np * Kp * 4 + 1024 <= 220 * 1024;
+}
+int b2no_tc_mix_dw_feasible(int batch, int ci, int co) {
+  if (!b2no_tc_available() || batch < g_mix_min_batch) return 0;
+  return 2 * ci <= 128 && b2no_round_up(2 * co, 16) <= 256;
+}
+
 int b2no_tc_mix(const b2no_plan* p, int mode, const float* in, const b2no_weights* w, float* out, int batch, int ci, int co,
                 int accumulate, cudaStream_t st) {
   if (!b2no_tc_available() || batch < g_mix_min_batch) return 1;
   MixTc q;
   memset(&q, 0, sizeof(q));
+  q.layout = p->g.spec_layout;
   q.B = batch; q.Cq = mode == 0 ? ci : co; q.Cp = mode == 0 ? co : ci; q.Kt = total_modes(p);
   q.Kp = b2no_round_up(2 * q.Cq, 16); q.Np = b2no_round_up(2 * q.Cp, 16);
   q.conjt = mode; q.accumulate = accumulate; q.npass = b2no_tc_passes();
@@ -400,7 +446,7 @@ int b2no_tc_mix_dw(const b2no_plan* p, const float* xh, const float* gyh, const 
   DwTc q;
   memset(&q, 0, sizeof(q));
   q.B = batch; q.Ci = ci; q.Co = co; q.Kt = total_modes(p); q.Np = b2no_round_up(2 * co, 16);
-  q.accumulate = accumulate; q.npass = b2no_tc_passes();
+  q.accumulate = accumulate; q.npass = b2no_tc_passes(); q.layout = p->g.spec_layout;
   q.xh = (const float2*)xh; q.gyh = (const float2*)gyh; q.w = *dw; q.mm = make_mode_map(p);
   if (2 * ci > 128 || q.Np > 256) return 1;
   q.Ga = (2 * ci + 7) / 8;

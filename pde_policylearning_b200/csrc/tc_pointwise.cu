@@ -447,15 +447,24 @@ constexpr int kInvHB = 32;
 template <int KXM, bool PAIR>   // KXM: compile-time bound on the kept rows Kx (register array size); PAIR: two modes per thread
 __global__ void __launch_bounds__(256)
 k_inv_h(const float2* __restrict__ spec, const float2* __restrict__ M, float* __restrict__ ahi, float* __restrict__ alo,
-        int Co, int Np, int Kx, int H, int Ky, int Qp) {
+        int Co, int Np, int Kx, int H, int Ky, int Qp, int layout) {
   extern __shared__ float2 s_spec[];  // [Co][Kx*Ky + 1] then the M rows of this block [Kx][kInvHB]
   const int b = blockIdx.y, h0 = blockIdx.x * kInvHB;
   const int kk = Kx * Ky, stride = kk + 1;
   float2* s_m = s_spec + (size_t)Co * stride;
   const float2* sp = spec + (size_t)b * Co * kk;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int o = warp; o < Co; o += 8)
-    for (int r = lane; r < kk; r += 32) s_spec[o * stride + r] = __ldg(sp + (size_t)o * kk + r);
+  if (layout == 0) {
+    for (int o = warp; o < Co; o += 8)
+      for (int r = lane; r < kk; r += 32) s_spec[o * stride + r] = __ldg(sp + (size_t)o * kk + r);
+  } else {
+    // mode-major spectrum (mode, batch, channel): a mode's Co values of this sample are contiguous
+    const size_t nb = gridDim.y;
+    for (int idx = threadIdx.x; idx < Co * kk; idx += 256) {
+      const int r = idx / Co, o = idx - r * Co;
+      s_spec[o * stride + r] = __ldg(spec + ((size_t)r * nb + b) * Co + o);
+    }
+  }
   for (int i = threadIdx.x; i < Kx * kInvHB; i += 256) {
     const int kx = i / kInvHB, hl = i - kx * kInvHB;
     s_m[i] = (h0 + hl < H) ? __ldg(M + (size_t)kx * H + h0 + hl) : make_float2(0.f, 0.f);
@@ -664,7 +673,7 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
   do {                                                                                                                  \
     if (smem > 48 * 1024) B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_inv_h<KXM, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     k_inv_h<KXM, PAIR><<<grid, 256, smem, st>>>((const float2*)spec, M, (float*)p.ahi, (float*)p.alo, channels, p.Np, plan->K[0], n[0], \
-                                                plan->K[1], p.Qp);                                                      \
+                                                plan->K[1], p.Qp, plan->g.spec_layout);                                 \
   } while (0)
 #define INVH_LAUNCH(KXM)                                                                                                \
   do {                                                                                                                  \

@@ -432,18 +432,20 @@ class RnoLayerFn(torch.autograd.Function):
         ops._require_cuda(x_tm, h0)
         x_tm, h0 = _contig(x_tm.float()), _contig(h0.float())
         Tn, B, Cc, H, W = x_tm.shape
-        plan = get_plan(geom, x_tm.device)
+        plan, geom = _rno_plan(geom, x_tm.device, B, Cc)
         pk = _rno_pack(params, Cc)
         xf = x_tm.reshape(Tn * B, Cc, H, W)
-        # ---- x side, batched over frames ----
+        # ---- x side, batched over whole frames ----
         Gzz2 = torch.empty((Tn * B, 2 * Cc, H, W), dtype=torch.float32, device=xf.device)
         Gr = torch.empty((Tn * B, Cc, H, W), dtype=torch.float32, device=xf.device)
         Gh = torch.empty_like(Gr)
-        Xh = torch.empty((Tn * B, Cc) + plan.kept, dtype=torch.complex64, device=xf.device)
-        for s in range(0, Tn * B, _RNO_XCHUNK):
-            e = min(Tn * B, s + _RNO_XCHUNK)
+        chunk = max(1, _RNO_XCHUNK // B) * B
+        Xh = []                                  # one spectrum per chunk (a mode-major spectrum cannot be sliced by batch)
+        for s in range(0, Tn * B, chunk):
+            e = min(Tn * B, s + chunk)
             xs = xf[s:e]
-            xh = ops.dft_forward(plan, 0, xs, out=Xh[s:e])
+            xh = ops.dft_forward(plan, 0, xs)
+            Xh.append(xh)
             for Wc, Pm, bias, co, G in ((pk["Wx_zz2"], pk["Px_zz2"], pk["bias_zz2"], 2 * Cc, Gzz2),
                                         (pk["Wx_r"], pk["Px_r"], pk["bias_r"], Cc, Gr),
                                         (pk["Wx_h"], pk["Px_h"], pk["bias_h"], Cc, Gh)):
@@ -475,8 +477,9 @@ class RnoLayerFn(torch.autograd.Function):
             h = hn
         ctx.geom, ctx.dims, ctx.return_sequences = geom, (Tn, B, Cc, H, W), return_sequences
         ctx.param_shapes = [tuple(p.shape) for p in params]
+        ctx.n_chunks, ctx.chunk = len(Xh), chunk
         if need_grad:
-            ctx.save_for_backward(xf, Xh, *[p.detach() for p in params], *saved)
+            ctx.save_for_backward(xf, *Xh, *[p.detach() for p in params], *saved)
         return torch.stack(hs, dim=0) if return_sequences else h
 
     @staticmethod
@@ -484,9 +487,10 @@ class RnoLayerFn(torch.autograd.Function):
         Tn, B, Cc, H, W = ctx.dims
         geom = ctx.geom
         sv = ctx.saved_tensors
-        xf, Xh = sv[0], sv[1]
-        params = sv[2:38]
-        steps = sv[38:]
+        nch = ctx.n_chunks
+        xf, Xh = sv[0], sv[1:1 + nch]
+        params = sv[1 + nch:37 + nch]
+        steps = sv[37 + nch:]
         plan = get_plan(geom, xf.device)
         pk = _rno_pack(params, Cc)
         dev = xf.device
@@ -543,9 +547,9 @@ class RnoLayerFn(torch.autograd.Function):
                   ("Wx_r", "Px_r", gGr.reshape(Tn * B, Cc, H, W), Cc),
                   ("Wx_h", "Px_h", gGh.reshape(Tn * B, Cc, H, W), Cc))
         firstc = True
-        for s in range(0, Tn * B, _RNO_XCHUNK):
-            e = min(Tn * B, s + _RNO_XCHUNK)
-            xs, xh = xf[s:e], Xh[s:e]
+        for j, s in enumerate(range(0, Tn * B, ctx.chunk)):
+            e = min(Tn * B, s + ctx.chunk)
+            xs, xh = xf[s:e], Xh[j]
             gX = None
             for wk, pkey, G, co in groups:
                 gs = G[s:e]
@@ -590,6 +594,20 @@ class RnoLayerFn(torch.autograd.Function):
             grads.append(v.sum().reshape(()))
         gx_out = gx.reshape(Tn, B, Cc, H, W) if need_x else None
         return (gx_out, g_h0, None, None) + tuple(grads)
+
+
+def _rno_plan(geom: SpecGeom, device, batch: int, channels: int):
+    """The plan of the RNO layer: mode-major spectra (the per-mode [batch x channel] slabs of the tensor-core mixing are
+    then contiguous) when every call of the layer is eligible for it, else the default layout."""
+    g1 = geom.with_layout(1)
+    try:
+        p1 = get_plan(g1, device)
+        if p1.layout_supported(batch, channels):
+            return p1, g1
+    except (RuntimeError, NotImplementedError):
+        pass
+    g0 = geom.with_layout(0)
+    return get_plan(g0, device), g0
 
 
 def _rno_pack(params, C):

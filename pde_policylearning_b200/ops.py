@@ -75,11 +75,16 @@ class SpecGeom:
     norm: str = "backward"
     nfft: Optional[Tuple[int, ...]] = None
     nout: Optional[Tuple[int, ...]] = None
+    # layout of the kept-mode spectra: 0 = (batch, channel, *kept), 1 = mode-major (*kept, batch, channel) -- see b2no_geom
+    layout: int = 0
 
     def resolved(self) -> "SpecGeom":
         nfft = tuple(self.nin) if self.nfft is None else tuple(self.nfft)
         nout = nfft if self.nout is None else tuple(self.nout)
-        return SpecGeom(tuple(self.nin), tuple(self.half), self.norm, nfft, nout)
+        return SpecGeom(tuple(self.nin), tuple(self.half), self.norm, nfft, nout, int(self.layout))
+
+    def with_layout(self, layout: int) -> "SpecGeom":
+        return SpecGeom(self.nin, self.half, self.norm, self.nfft, self.nout, int(layout))
 
     @property
     def ndim(self):
@@ -112,6 +117,7 @@ class Plan:
         for j in range(g.ndim):
             cg.nin[j], cg.nfft[j], cg.nout[j], cg.half[j] = g.nin[j], g.nfft[j], g.nout[j], g.half[j]
         cg.norm = NORM[g.norm]
+        cg.spec_layout = int(g.layout)
         handle = C.c_void_p()
         with torch.cuda.device(device):
             check(_lib.lib().b2no_plan_create(C.byref(cg), C.byref(handle)), "plan_create")
@@ -123,6 +129,23 @@ class Plan:
         self.kept = tuple(int(kept[j]) for j in range(g.ndim))
         self.modes = math.prod(self.kept)
         self.s_f, self.s_i = g.scales()
+        self.layout = int(g.layout)
+
+    def spec_shape(self, batch: int, channels: int):
+        return (self.kept + (batch, channels)) if self.layout else ((batch, channels) + self.kept)
+
+    def spec_bc(self, spec: torch.Tensor):
+        """(batch, channels) of a spectrum tensor of this plan's layout."""
+        if self.layout:
+            if tuple(spec.shape[:-2]) != self.kept:
+                raise ValueError(f"expected kept modes {self.kept} (mode-major), got {tuple(spec.shape)}")
+            return int(spec.shape[-2]), int(spec.shape[-1])
+        if tuple(spec.shape[2:]) != self.kept:
+            raise ValueError(f"expected kept modes {self.kept}, got {tuple(spec.shape[2:])}")
+        return int(spec.shape[0]), int(spec.shape[1])
+
+    def layout_supported(self, batch: int, channels: int) -> bool:
+        return bool(_lib.lib().b2no_plan_layout_supported(self.handle, batch, channels))
 
     def workspace(self, batch: int, channels: int) -> Optional[torch.Tensor]:
         n = int(_lib.lib().b2no_plan_workspace_floats(self.handle, batch, channels))
@@ -194,10 +217,10 @@ def dft_forward(plan: Plan, which: int, x: torch.Tensor, out: Optional[torch.Ten
     if tuple(x.shape[2:]) != tuple(grid):
         raise ValueError(f"expected grid {tuple(grid)}, got {tuple(x.shape[2:])}")
     if out is None:
-        spec = torch.empty((B, Cc) + plan.kept, dtype=torch.complex64, device=x.device)
+        spec = torch.empty(plan.spec_shape(B, Cc), dtype=torch.complex64, device=x.device)
     else:
         spec = out
-        assert spec.dtype == torch.complex64 and spec.is_contiguous() and tuple(spec.shape) == (B, Cc) + plan.kept
+        assert spec.dtype == torch.complex64 and spec.is_contiguous() and tuple(spec.shape) == plan.spec_shape(B, Cc)
     work = plan.workspace(B, Cc)
     check(_lib.lib().b2no_dft_forward(plan.handle, which, _ptr(x), _ptr(spec), _ptr(work), B * Cc, _stream()),
           "dft_forward")
@@ -244,9 +267,7 @@ def dft_inverse(plan: Plan, which: int, spec: torch.Tensor, epi: Optional[Epilog
     """spectrum (B, C, *kept) complex64 -> y (B, C, *grid) fp32, with the fused epilogue."""
     _require_cuda(spec)
     assert spec.dtype == torch.complex64 and spec.is_contiguous()
-    B, Cc = spec.shape[:2]
-    if tuple(spec.shape[2:]) != plan.kept:
-        raise ValueError(f"expected kept modes {plan.kept}, got {tuple(spec.shape[2:])}")
+    B, Cc = plan.spec_bc(spec)
     grid = plan.geom.nout if which == 0 else plan.geom.nin
     y = out if out is not None else torch.empty((B, Cc) + tuple(grid), dtype=torch.float32, device=spec.device)
     work = plan.workspace(B, Cc)
@@ -268,11 +289,11 @@ def mix(plan: Plan, mode: int, spec: torch.Tensor, corners: Sequence[torch.Tenso
         out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
     _require_cuda(spec)
     assert spec.dtype == torch.complex64 and spec.is_contiguous()
-    B = spec.shape[0]
+    B, cspec = plan.spec_bc(spec)
     cin, cout = (ci, co) if mode == 0 else (co, ci)
-    assert spec.shape[1] == cin, (spec.shape, cin)
+    assert cspec == cin, (spec.shape, cin)
     if out is None:
-        out = torch.empty((B, cout) + plan.kept, dtype=torch.complex64, device=spec.device)
+        out = torch.empty(plan.spec_shape(B, cout), dtype=torch.complex64, device=spec.device)
         accumulate = False
     w = weights_struct(corners, plan.geom.ndim)
     check(_lib.lib().b2no_mix(plan.handle, mode, _ptr(spec), C.byref(w), _ptr(out), B, ci, co,
@@ -284,8 +305,8 @@ def mix_dw(plan: Plan, xh: torch.Tensor, gyh: torch.Tensor, like: Sequence[torch
            out: Optional[Sequence[torch.Tensor]] = None, accumulate: bool = False):
     """Returns the list of corner gradients shaped/typed like `like`; with `out` (contiguous tensors of that shape) the
     gradients are written -- or, with accumulate, added -- in place (BPTT over the recurrent steps of the RNO)."""
-    B, ci = xh.shape[:2]
-    co = gyh.shape[1]
+    B, ci = plan.spec_bc(xh)
+    co = plan.spec_bc(gyh)[1]
     if out is None:
         alloc = torch.zeros_like if needs_zero else torch.empty_like
         grads = [alloc(t, memory_format=torch.contiguous_format) for t in like]

@@ -2,7 +2,7 @@
 # gpurun call d: tests of the changed kernels, quick timings (fp32 / tf32 mode), ncu full captures
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
-for k in tensor_core_mixing regrouped golden_rno single_a_buffer tensor_core_tile_kernel gate_epilogue; do
+for k in mode_major tensor_core_mixing regrouped golden_rno cfg3_rno_full_size gate_epilogue; do
   timeout -s KILL 240 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 200 --tb=short -s -k "$k" > gpurun_out/pt_$k.log 2>&1
   echo "[$k] rc=$? $(grep -E 'passed|failed|error' gpurun_out/pt_$k.log | tail -1)"
   grep -E "^E  |Error|error:" gpurun_out/pt_$k.log | head -6

@@ -29,6 +29,29 @@ class _Plan:
         self.modes = math.prod(self.kept)
         self.s_f, self.s_i = self.cf.scales()
         self.device = torch.device("cpu")
+        self.layout = int(getattr(g, "layout", 0))
+
+    def layout_supported(self, batch, channels):
+        return self.layout == 0 or self.geom.ndim == 2      # exercise the mode-major host logic on the CPU too
+
+    def spec_shape(self, batch, channels):
+        return (self.kept + (batch, channels)) if self.layout else ((batch, channels) + self.kept)
+
+    def spec_bc(self, spec):
+        return (int(spec.shape[-2]), int(spec.shape[-1])) if self.layout else (int(spec.shape[0]), int(spec.shape[1]))
+
+    def to_std(self, spec):
+        """-> (batch, channel, *kept)"""
+        if not self.layout:
+            return spec
+        d = len(self.kept)
+        return spec.permute(d, d + 1, *range(d))
+
+    def from_std(self, spec):
+        if not self.layout:
+            return spec
+        d = len(self.kept)
+        return spec.permute(*range(2, 2 + d), 0, 1).contiguous()
 
 
 _plans = {}
@@ -66,7 +89,7 @@ def _act_grad(z, act):
 
 def dft_forward(plan, which, x, out=None):
     spec = cf.dft_trunc(plan.cf, x, plan.s_f) if which == 0 else cf.dft_trunc(plan.cf, x, plan.s_i, use_inv_conj=True)
-    spec = spec.to(torch.complex64)
+    spec = plan.from_std(spec.to(torch.complex64))
     if out is not None:
         out.copy_(spec)
         return out
@@ -109,6 +132,7 @@ def _epilogue(z, epi, channels, grid):
 
 
 def dft_inverse(plan, which, spec, epi=None, out=None):
+    spec = plan.to_std(spec)
     z = cf.idft_trunc(plan.cf, spec, plan.s_i) if which == 0 else cf.idft_trunc(plan.cf, spec, plan.s_f, use_fwd_conj=True)
     grid = plan.geom.nout if which == 0 else plan.geom.nin
     y = _epilogue(z, epi, spec.shape[1], tuple(grid))
@@ -125,12 +149,12 @@ def pointwise(batch, channels, grid, device, epi):
 
 def mix(plan, mode, spec, corners, ci, co, out=None, accumulate=False):
     W = cf.gather_weight(plan.cf, [_cplx(c) for c in corners])
-    s = spec.to(CD)
+    s = plan.to_std(spec).to(CD)
     if mode == 0:
         r = torch.einsum("bi...,io...->bo...", s, W)
     else:
         r = torch.einsum("bo...,io...->bi...", s, W.conj())
-    r = r.to(torch.complex64)
+    r = plan.from_std(r.to(torch.complex64))
     if out is not None:
         if accumulate:
             out.add_(r)
@@ -141,7 +165,7 @@ def mix(plan, mode, spec, corners, ci, co, out=None, accumulate=False):
 
 
 def mix_dw(plan, xh, gyh, like, needs_zero, out=None, accumulate=False):
-    dW_eff = torch.einsum("bi...,bo...->io...", xh.to(CD).conj(), gyh.to(CD))
+    dW_eff = torch.einsum("bi...,bo...->io...", plan.to_std(xh).to(CD).conj(), plan.to_std(gyh).to(CD))
     shapes = [tuple(t.shape if t.is_complex() else t.shape[:-1]) for t in like]
     dW = cf.scatter_weight_grad(plan.cf, dW_eff, shapes)
     res = []

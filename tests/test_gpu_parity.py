@@ -1084,3 +1084,40 @@ def test_cfg4_pino_full_size_vs_restated():
           f"{abs(loss.item() - loss64.item()) / abs(loss64.item()):.2e}, worst gradient {worst:.2e} (reference fp32: {worst32:.2e})")
     assert eo < 2e-5, eo
     assert abs(loss.item() - loss64.item()) < 2e-5 * abs(loss64.item())
+
+
+def test_mode_major_spectrum_layout():
+    """b2no_geom.spec_layout = 1 (kept modes outermost): every op of the RNO layer -- forward DFT, its adjoint twin, mixing,
+    adjoint mixing (plain and accumulated), dW (plain and accumulated), inverse with epilogue -- gives bit-for-bit the same
+    numbers as the default layout (same kernels, different addressing), at the cfg3 layer shape."""
+    from pde_policylearning_b200 import ops
+    dev = _dev()
+    torch.manual_seed(21)
+    g0 = ops.SpecGeom(nin=(32, 32), half=(12, 12), norm="ortho")
+    p0, p1 = ops.get_plan(g0, dev), ops.get_plan(g0.with_layout(1), dev)
+    B, C = 160, 34
+    assert p1.layout_supported(B, C)
+    mm = lambda s: s.permute(2, 3, 0, 1).contiguous()            # (B, C, Kx, Ky) -> (Kx, Ky, B, C)
+    x = torch.randn(B, C, 32, 32, device=dev)
+    w = [torch.randn(C, 2 * C, 12, 12, 2, device=dev) * 0.1 for _ in range(2)]
+    pw = torch.randn(2 * C, C, device=dev) * 0.2
+    add = torch.randn(B, 2 * C, 32, 32, device=dev)
+    for which in (0, 1):
+        a, b = ops.dft_forward(p0, which, x), ops.dft_forward(p1, which, x)
+        assert b.shape == (24, 12, B, C) and torch.equal(mm(a), b), which
+    xh0 = ops.dft_forward(p0, 0, x)
+    xh1 = mm(xh0)
+    y0, y1 = ops.mix(p0, 0, xh0, w, C, 2 * C), ops.mix(p1, 0, xh1, w, C, 2 * C)
+    assert y1.shape == (24, 12, B, 2 * C) and rel(y1, mm(y0)) < 1e-7
+    gx0, gx1 = ops.mix(p0, 1, y0, w, C, 2 * C), ops.mix(p1, 1, y1, w, C, 2 * C)
+    assert rel(gx1, mm(gx0)) < 1e-7
+    acc1 = ops.mix(p1, 1, y1, w, C, 2 * C, out=gx1.clone(), accumulate=True)
+    assert rel(acc1, 2 * mm(gx0)) < 1e-6
+    d0 = ops.mix_dw(p0, xh0, y0, w, needs_zero=False)
+    d1 = ops.mix_dw(p1, xh1, y1, w, needs_zero=False)
+    assert all(rel(a, b) < 1e-6 for a, b in zip(d1, d0))
+    ops.mix_dw(p1, xh1, y1, w, needs_zero=False, out=d1, accumulate=True)
+    assert all(rel(a, 2 * b) < 1e-6 for a, b in zip(d1, d0))
+    e = lambda: ops.make_epilogue(pw_w=pw, pw_x=x, add=add, act="sigmoid")
+    z0, z1 = ops.dft_inverse(p0, 0, y0, e()), ops.dft_inverse(p1, 0, mm(y0), e())
+    assert torch.equal(z0, z1)
