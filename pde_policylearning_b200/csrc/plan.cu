@@ -326,7 +326,12 @@ extern "C" int64_t b2no_plan_workspace_floats(const b2no_plan* p, int64_t batch,
     a *= p->K[d - 1];
     if (d == 3) b = bc * n[0] * p->K[1] * p->K[2];
     int64_t tot = 2 * (a + b);
-    if (d == 3) tot += bc * n[0] * n[1] * n[2];       // T: the transform's result handed to the pointwise tile kernel
+    if (d == 3) {
+      tot += bc * n[0] * n[1] * n[2];       // T: the transform's result handed to the pointwise tile kernel (split path)
+      // row image of the fused path: [batch][n0 * n1 rows][Qp][Np] + the rows the last tiles read past the end
+      const int64_t qp = (2 * p->K[2] + 7) / 8 * 8, np = (channels + 15) / 16 * 16, r = 127 / n[2] + 3;
+      tot += (batch * n[0] * n[1] + r) * qp * np;
+    }
     if (tot > best) best = tot;
     // tensor-core path: A' rows (hi + lo), [batch][rows][Qp][channels rounded up to 16]
     if (d == 2 && p->tc[which].timg) {

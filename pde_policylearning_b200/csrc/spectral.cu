@@ -1022,6 +1022,14 @@ extern "C" int b2no_dft_inverse(const b2no_plan* p, int which, const float* spec
   const float2* T0 = which == 0 ? p->m_inv[0] : p->m_adjfwd[0];
   int rc = run_cmat((const float2*)spec, Bb, T0, bc, p->K[0], n[0], p->K[1] * Kl, st);
   if (rc) return rc;
+  // 3-D, fused: the middle-dim stage writes the row image (k_inv_h) and the tile kernel does the last dim itself, with a
+  // per-tile T operand built by its converter warps -- the transform's result never exists in HBM (this replaced the
+  // k_c2r_plain8 pass + the T round trip below: 1.5 ms + 0.4 ms of the 9.6 ms PINO step).
+  if (epi && e.pw_ci > 0 && b2no_tc_available() && P % 128 == 0) {
+    float* img = work + 2 * ((size_t)bc * n[0] * n[1] * Kl + (size_t)bc * n[0] * p->K[1] * Kl) + (size_t)bc * P;
+    const int rc3 = b2no_tc_pointwise(p, which, (const float*)Bb, y, img, batch, channels, P, epi, st);
+    if (rc3 != 1) return rc3;
+  }
   const float2* T1 = which == 0 ? p->m_inv[1] : p->m_adjfwd[1];
   rc = run_cmat(Bb, A, T1, bc * n[0], p->K[1], n[1], Kl, st);
   if (rc) return rc;

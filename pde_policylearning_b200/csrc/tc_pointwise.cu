@@ -58,10 +58,16 @@ struct PwTc {
   int act, dact;
   int debug;          // bit0 no stores, bit1 no MMAs
   int npass;          // 3: 3xTF32, 1: single-pass TF32 (hi * hi only)
+  // 3-D mode (zlen > 0): rows of the last dim have zlen points, a 128-pixel tile touches up to R = 127 / zlen + 2 of them.
+  // The last-stage operand T[pixel, (row slot, q)] then depends on where the tile starts, so the converter warps build it
+  // per tile from the plan's [q][z] table (staged hi / lo in shared memory) instead of loading one constant image.
+  int zlen, q2, tz_npad;
+  long RPI;           // rows per sample (n0 * n1)
+  const float* tz;
 };
 
 struct PwLayout {
-  uint32_t w1h, w1l, w2h, w2l, bias, stages, stage_bytes, x2, ah, al, dz, bars, total;
+  uint32_t w1h, w1l, w2h, w2l, bias, tzh, tzl, stages, stage_bytes, x2, ah, al, dz, bars, total;
 };
 
 __host__ __device__ inline PwLayout pw_layout(const PwTc& p) {
@@ -72,6 +78,8 @@ __host__ __device__ inline PwLayout pw_layout(const PwTc& p) {
   L.w1h = o; o += wb1; L.w1l = o; o += wb1;
   L.w2h = o; o += wb2; L.w2l = o; o += wb2;
   L.bias = o; o += (uint32_t)p.Np * 4;
+  L.tzh = o; o += (uint32_t)p.Qp * p.zlen * 4;       // 3-D mode: last-dim table [q][z], hi then lo
+  L.tzl = o; o += (uint32_t)p.Qp * p.zlen * 4;
   o = (o + 1023u) & ~1023u;
   L.stages = o;
   L.x2 = xb1; L.ah = xb1 + xb2; L.al = L.ah + ab;
@@ -85,6 +93,7 @@ __host__ __device__ inline PwLayout pw_layout(const PwTc& p) {
 }
 
 __host__ __device__ inline uint32_t pw_tmem_cols(const PwTc& p) {
+  if (p.zlen) return 2u * p.Np + (uint32_t)p.NA * (2u * (p.C1p + p.C2p) + 2u * p.Ks);   // T lives in the per-tile operand buffer
   return 2u * p.Np + 2u * p.Ks + 2u * (uint32_t)p.NA * (p.C1p + p.C2p);
 }
 
@@ -136,6 +145,13 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
     *(float*)(smem + L.w2l + kmajor_off(n, k, p.C2p)) = tf32_rna(w - hi);
   }
   for (int i = tid; i < p.Np; i += kThreads) ((float*)(smem + L.bias))[i] = (p.bias && i < p.Co) ? p.bias[i] : 0.f;
+  for (int i = tid; i < p.Qp * p.zlen; i += kThreads) {
+    const int q = i / p.zlen, z = i - q * p.zlen;
+    const float v = q < p.q2 ? p.tz[(size_t)q * p.tz_npad + z] : 0.f;
+    const float hi = tf32_rna(v);
+    ((float*)(smem + L.tzh))[i] = hi;
+    ((float*)(smem + L.tzl))[i] = tf32_rna(v - hi);
+  }
   if (tid == 0) {
     // a stage is free when its MMAs have completed and (dz ring) every epilogue thread has taken its dz values
     for (int s = 0; s < p.S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1 + ((MODE == 3 && p.Cz) ? kEpiThreadsPw : 0)); }
@@ -152,8 +168,10 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = *tslot;
-  const uint32_t t_hi = tbase + 2u * p.Np, t_lo = t_hi + p.Ks;
-  const uint32_t a_base = t_lo + p.Ks, a_width = 2u * (p.C1p + p.C2p);
+  const uint32_t t_hi = tbase + 2u * p.Np, t_lo = t_hi + p.Ks;                       // 2-D: the constant T operand
+  const uint32_t x_width = 2u * (p.C1p + p.C2p);
+  const uint32_t a_base = p.zlen ? tbase + 2u * p.Np : t_lo + p.Ks;
+  const uint32_t a_width = p.zlen ? x_width + 2u * p.Ks : x_width;                    // 3-D: [X hi | lo ...][T hi | T lo] per buffer
 
   const uint32_t xb1 = (uint32_t)p.C1p * 512, xb2 = (uint32_t)p.C2p * 512, ab = (uint32_t)p.Ks * p.Np * 4;
   // each CTA owns a contiguous run of tiles (sequential DRAM pages per channel row, same sample for A')
@@ -177,7 +195,9 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
         if (p.C2p) tma_load_3d(st + L.x2, &tm2, &full[s], t_in_img * 128, 0, b);
         if (MODE == 3 && p.Cz) tma_load_3d(st + L.dz, &tm3, &full[s], t_in_img * 128, 0, b);
         if (p.Ks) {
-          const size_t off = (size_t)tile * p.R * p.Qp * p.Np;
+          // 2-D: the tile's R whole rows; 3-D: the R rows the tile touches, from the row of its first pixel on
+          const size_t off = p.zlen ? ((size_t)b * p.RPI + (size_t)(t_in_img * 128) / p.zlen) * p.Qp * p.Np
+                                    : (size_t)tile * p.R * p.Qp * p.Np;
           bulk_load(st + L.ah, p.ahi + off, ab, &full[s]);     // fp32 image; the converter warps split it into hi | lo
         }
       }
@@ -236,7 +256,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
             const uint64_t d_al = smem_desc(st + L.al, lbo_a, 128, LAYOUT_NONE);
             _Pragma("unroll") for (int pass = 0; pass < 3; pass++) {
             if (pass >= p.npass) break;   // compile-time trip count (descriptors stay folded); 1-pass mode leaves early
-              const uint32_t tcn = pass == 1 ? t_lo : t_hi;
+              const uint32_t tcn = p.zlen ? (pass == 1 ? xa + x_width + p.Ks : xa + x_width) : (pass == 1 ? t_lo : t_hi);
               const uint64_t da = pass == 2 ? d_al : d_ah;
               for (int k = 0; k < p.Ks / 8; k++)
                 mma_tf32_ts(d, tcn + 8 * k, da + (uint64_t)(k * (2 * lbo_a / 16)), idesc, 1);
@@ -256,8 +276,8 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
     const int quad = warp & 3;
     const int m = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    // constant T operand, once
-    for (int c0 = 0; c0 < p.Ks; c0 += 8) {
+    // constant T operand, once (2-D)
+    for (int c0 = 0; c0 < (p.zlen ? 0 : p.Ks); c0 += 8) {
       float hi[8], lo[8];
 #pragma unroll
       for (int j = 0; j < 8; j++) {
@@ -312,6 +332,28 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
           }
           tmem_st8(xa + 2 * p.C1p + c0, hi);
           tmem_st8(xa + 2 * p.C1p + p.C2p + c0, lo);
+        }
+      }
+      if (p.zlen) {
+        // 3-D: T[m, (slot, q)] = table[q][z(m)] in the slot of pixel m's row, zero elsewhere
+        const long tin = tile % p.tiles_per_img;
+        const long pix = tin * 128 + m;
+        const int r0 = (int)((tin * 128) / p.zlen);
+        const int slot = (int)(pix / p.zlen) - r0, z = (int)(pix % p.zlen);
+        const float* th = (const float*)(smem + L.tzh);
+        const float* tl = (const float*)(smem + L.tzl);
+        const uint32_t ta = xa + x_width;
+        for (int c0 = 0; c0 < p.Ks; c0 += 8) {
+          float hi[8], lo[8];
+          const int sl = c0 / p.Qp, q0 = c0 - sl * p.Qp;      // Qp is a multiple of 8: a chunk never straddles slots
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const bool on = sl == slot;
+            hi[j] = on ? th[(q0 + j) * p.zlen + z] : 0.f;
+            lo[j] = on ? tl[(q0 + j) * p.zlen + z] : 0.f;
+          }
+          tmem_st8(ta + c0, hi);
+          tmem_st8(ta + p.Ks + c0, lo);
         }
       }
       tmem_st_wait();
@@ -447,7 +489,7 @@ constexpr int kInvHB = 32;
 template <int KXM, bool PAIR>   // KXM: compile-time bound on the kept rows Kx (register array size); PAIR: two modes per thread
 __global__ void __launch_bounds__(256)
 k_inv_h(const float2* __restrict__ spec, const float2* __restrict__ M, float* __restrict__ ahi, float* __restrict__ alo,
-        int Co, int Np, int Kx, int H, int Ky, int Qp, int layout) {
+        int Co, int Np, int Kx, int H, int Ky, int Qp, int layout, int n0) {
   extern __shared__ float2 s_spec[];  // [Co][Kx*Ky + 1] then the M rows of this block [Kx][kInvHB]
   const int b = blockIdx.y, h0 = blockIdx.x * kInvHB;
   const int kk = Kx * Ky, stride = kk + 1;
@@ -457,6 +499,13 @@ k_inv_h(const float2* __restrict__ spec, const float2* __restrict__ M, float* __
   if (layout == 0) {
     for (int o = warp; o < Co; o += 8)
       for (int r = lane; r < kk; r += 32) s_spec[o * stride + r] = __ldg(sp + (size_t)o * kk + r);
+  } else if (layout == 2) {
+    // 3-D: "sample" = (b, x); the x-stage output is [(b, channel, x)][K1][K2] -- the middle-dim inverse of the PINO layer
+    const int b3 = b / n0, x = b - b3 * n0;
+    for (int o = warp; o < Co; o += 8) {
+      const float2* so = spec + (((size_t)b3 * Co + o) * n0 + x) * kk;
+      for (int r = lane; r < kk; r += 32) s_spec[o * stride + r] = __ldg(so + r);
+    }
   } else {
     // mode-major spectrum (mode, batch, channel): a mode's Co values of this sample are contiguous
     const size_t nb = gridDim.y;
@@ -600,7 +649,8 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
   p.gate_z = (e->gate_z && e->gate_h) ? e->gate_z : nullptr; p.gate_h = p.gate_z ? e->gate_h : nullptr;
   p.mul_bs = e->mul_bstride ? (long)e->mul_bstride : (long)channels * pixels;
   p.gate_bs = e->gate_bstride ? (long)e->gate_bstride : (long)channels * pixels;
-  if (spec) {
+  const bool three_d = spec && plan && plan->g.ndim == 3;
+  if (spec && !three_d) {
     if (!plan || plan->g.ndim != 2 || !work) return 1;
     const b2no_tc_tables& tt = plan->tc[which];
     if (!tt.timg) return 1;
@@ -610,6 +660,21 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
     const size_t afl = (size_t)batch * n[0] * p.Qp * p.Np;
     p.ahi = work;
     p.alo = work + afl;
+  }
+  if (three_d) {
+    // 3-D: `spec` is the x-stage output [(b, channel, x)][K1][K2]; k_inv_h does the middle-dim stage into the row image,
+    // the tile kernel the last dim with a per-tile T operand (rows of n2 points do not align with 128-pixel tiles)
+    if (!work) return 1;
+    const int32_t* n = which == 0 ? plan->g.nout : plan->g.nin;
+    if ((long)n[0] * n[1] * n[2] != pixels) return B2NO_E_ARG;
+    p.zlen = n[2]; p.q2 = 2 * plan->K[2]; p.Qp = b2no_round_up(p.q2, 8);
+    p.R = 127 / p.zlen + 2; p.Ks = p.R * p.Qp;
+    p.RPI = (long)n[0] * n[1];
+    p.tz = which == 0 ? plan->t_out : plan->t_in;
+    p.tz_npad = which == 0 ? plan->npad_out : plan->npad_in;
+    if (p.zlen < 8 || p.Ks > 192 || plan->K[1] > 32 || p.Qp > 64) return 1;
+    p.ahi = work;
+    p.alo = work;
   }
   p.NA = 2;
   if (pw_tmem_cols(p) > 512) p.NA = 1;          // wide operands: one A buffer (the converter then waits for the tile's MMAs)
@@ -664,22 +729,31 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
   }
   if (spec) {
     const int32_t* n = which == 0 ? plan->g.nout : plan->g.nin;
-    const float2* M = which == 0 ? plan->m_inv[0] : plan->m_adjfwd[0];
-    const size_t smem = ((size_t)channels * (plan->K[0] * plan->K[1] + 1) + (size_t)plan->K[0] * kInvHB) * sizeof(float2);
+    // the stage k_inv_h contracts: dim 0 of a 2-D plan, dim 1 of a 3-D one (its "samples" are then the (b, x) pairs)
+    const int jd = three_d ? 1 : 0;
+    const float2* M = which == 0 ? plan->m_inv[jd] : plan->m_adjfwd[jd];
+    const int ikx = plan->K[jd], iky = plan->K[jd + 1], ih = n[jd];
+    const int ilayout = three_d ? 2 : plan->g.spec_layout, in0 = three_d ? n[0] : 1;
+    const size_t smem = ((size_t)channels * (ikx * iky + 1) + (size_t)ikx * kInvHB) * sizeof(float2);
     if (smem > 200 * 1024) return 1;
-    dim3 grid((unsigned)((n[0] + kInvHB - 1) / kInvHB), (unsigned)batch);
+    if ((long)batch * in0 > 65535) return 1;
+    dim3 grid((unsigned)((ih + kInvHB - 1) / kInvHB), (unsigned)(batch * in0));
+    if (three_d) {
+      // the tiles at the end of the image read up to R rows past it: keep those finite (they meet zero T entries)
+      B2NO_CHECK_CUDA(cudaMemsetAsync(work + (size_t)batch * p.RPI * p.Qp * p.Np, 0, (size_t)(p.R + 1) * p.Qp * p.Np * sizeof(float), st));
+    }
     const bool pair = (p.Qp / 4) * (p.Np / 8) * 8 >= 256;      // enough two-mode slots for every thread of the block
 #define INVH_LAUNCH1(KXM, PAIR)                                                                                         \
   do {                                                                                                                  \
     if (smem > 48 * 1024) B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_inv_h<KXM, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_inv_h<KXM, PAIR><<<grid, 256, smem, st>>>((const float2*)spec, M, (float*)p.ahi, (float*)p.alo, channels, p.Np, plan->K[0], n[0], \
-                                                plan->K[1], p.Qp, plan->g.spec_layout);                                 \
+    k_inv_h<KXM, PAIR><<<grid, 256, smem, st>>>((const float2*)spec, M, (float*)p.ahi, (float*)p.alo, channels, p.Np, ikx, ih, \
+                                                iky, p.Qp, ilayout, in0);                                               \
   } while (0)
 #define INVH_LAUNCH(KXM)                                                                                                \
   do {                                                                                                                  \
     if (pair) INVH_LAUNCH1(KXM, true); else INVH_LAUNCH1(KXM, false);                                                   \
   } while (0)
-    const int kx = plan->K[0];
+    const int kx = ikx;
     if (kx <= 8) INVH_LAUNCH(8);
     else if (kx <= 12) INVH_LAUNCH(12);
     else if (kx <= 16) INVH_LAUNCH(16);
