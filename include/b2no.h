@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define B2NO_MAX_DIM 3
-#define B2NO_ABI_VERSION 4
+#define B2NO_ABI_VERSION 5
 
 enum { B2NO_NORM_BACKWARD = 0, B2NO_NORM_FORWARD = 1, B2NO_NORM_ORTHO = 2 };
 enum { B2NO_ACT_NONE = 0, B2NO_ACT_GELU = 1, B2NO_ACT_RELU = 2, B2NO_ACT_SIGMOID = 3, B2NO_ACT_SELU = 4,
@@ -171,6 +171,18 @@ int b2no_mlp_head_bwd_supported(int ci, int hidden, int64_t pixels);
 int b2no_mlp_head_bwd(const float* x, const float* w1, const float* b1, const float* w2, const float* g, float* gx,
                       float* gz, float* dw2, float* partial, int batch, int ci, int hidden, int64_t pixels,
                       int b1_per_sample, int act, const float* dact_z, int dact, void* stream);
+/* WHOLE backward of the fused head in one kernel (same reference lines; replaces b2no_mlp_head_bwd + b2no_pw_wgrad on the
+ * hidden-channel gradient): f is recomputed on the tensor cores and never written to memory.
+ *   gx[b,i,p] as above;  grads = [ dW1 (hidden x ci) | db1 (hidden) | dw2 (hidden) ] contiguous floats:
+ *   dW1[j,i] = sum_{b,p} f[b,j,p] x[b,i,p];  db1[j] = sum_{b,p} f[b,j,p];  dw2[j] = sum_{b,p} g[b,p] act(z1[b,j,p]).
+ * b1 is (hidden) (a per-sample bias keeps the two-kernel path).  partial: b2no_mlp_head_bwd_fused_scratch_floats(ci, hidden)
+ * floats.  Shapes: ci <= 32, hidden <= 256, pixels % 128 == 0 (b2no_mlp_head_bwd_fused_supported); otherwise
+ * B2NO_E_UNSUPPORTED. */
+int64_t b2no_mlp_head_bwd_fused_scratch_floats(int ci, int hidden);
+int b2no_mlp_head_bwd_fused_supported(int ci, int hidden, int64_t pixels);
+int b2no_mlp_head_bwd_fused(const float* x, const float* w1, const float* b1, const float* w2, const float* g, float* gx,
+                            float* grads, float* partial, int batch, int ci, int hidden, int64_t pixels, int act,
+                            const float* dact_z, int dact, void* stream);
 /* RNO gate (rno.py:259): h_next = (1 - z) * h + z2 * hhat, and its backward */
 int b2no_rno_gate_fwd(const float* z, const float* z2, const float* hhat, const float* h, float* out,
                       int64_t n, void* stream);

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # B2NO_LIB: load another build of the same sources (A/B measurements of compile-time switches)
 LIB_PATH = os.environ.get("B2NO_LIB") or os.path.join(_HERE, "libb2no.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["plan.cu", "spectral.cu", "pointwise.cu", "tc_pointwise.cu", "tc_wgrad.cu", "tc_mlp.cu", "tc_dft.cu", "tc_mix.cu", "tc_peak.cu", "pino_loss.cu", "optim.cu"]
+SOURCES = ["plan.cu", "spectral.cu", "pointwise.cu", "tc_pointwise.cu", "tc_wgrad.cu", "tc_mlp.cu", "tc_head_bwd.cu", "tc_dft.cu", "tc_mix.cu", "tc_peak.cu", "pino_loss.cu", "optim.cu"]
 
 MAX_DIM = 3
 NORM = {"backward": 0, "forward": 1, "ortho": 2}
@@ -120,6 +120,10 @@ def lib():
     L.b2no_mlp_head_bwd_scratch_floats.restype = i64
     L.b2no_mlp_head_bwd_scratch_floats.argtypes = [i32]
     L.b2no_mlp_head_bwd.argtypes = [vp] * 9 + [i32, i32, i32, i64, i32, i32, vp, i32, vp]
+    L.b2no_mlp_head_bwd_fused_supported.argtypes = [i32, i32, i64]
+    L.b2no_mlp_head_bwd_fused_scratch_floats.restype = i64
+    L.b2no_mlp_head_bwd_fused_scratch_floats.argtypes = [i32, i32]
+    L.b2no_mlp_head_bwd_fused.argtypes = [vp] * 8 + [i32, i32, i32, i64, i32, vp, i32, vp]
     L.b2no_rno_gate_fwd.argtypes = [vp, vp, vp, vp, vp, i64, vp]
     L.b2no_rno_gate_bwd.argtypes = [vp] * 9 + [i64, vp]
     L.b2no_rno_cell_bwd.argtypes = [vp] * 7 + [i32, i32, i64, vp]
@@ -148,6 +152,7 @@ EXPORTS = [
     "b2no_set_tensor_core_mode", "b2no_set_precision", "b2no_tensor_core_launches", "b2no_kernel_launches",
     "b2no_dft_forward", "b2no_dft_inverse", "b2no_mix", "b2no_mix_dw",
     "b2no_act_bwd", "b2no_pw_wgrad_scratch_floats", "b2no_pw_wgrad", "b2no_mlp_head_fwd", "b2no_mlp_head_bwd_scratch_floats", "b2no_mlp_head_bwd_supported", "b2no_mlp_head_bwd",
+    "b2no_mlp_head_bwd_fused_scratch_floats", "b2no_mlp_head_bwd_fused_supported", "b2no_mlp_head_bwd_fused",
     "b2no_rno_gate_fwd", "b2no_rno_gate_bwd", "b2no_rno_cell_bwd", "b2no_rno_reset_bwd", "b2no_rel_l2_sums", "b2no_rel_l2_bwd",
     "b2no_rel_l2_finish", "b2no_rel_l2_bwd_g", "b2no_adam_step", "b2no_gather_segments",
     "b2no_tc_peak_probe", "b2no_pino_residual_scratch_floats", "b2no_pino_residual_fwd", "b2no_pino_residual_bwd",

@@ -303,6 +303,15 @@ class MlpHeadFn(torch.autograd.Function):
         x, w1m, b1c, w2v = ctx.saved_tensors
         g = _contig(g.float())
         need_x, need_w1, need_b1, need_w2, need_b2 = ctx.needs_input_grad[:5]
+        per_sample_b1 = b1c is not None and b1c.dim() == 2
+        if (not per_sample_b1 and g.data_ptr() % 16 == 0
+                and ops.mlp_head_bwd_fused_supported(x.shape[1], w1m.shape[0], math.prod(x.shape[2:]))):
+            # one kernel: gx, dW1, db1, dw2 (csrc/tc_head_bwd.cu)
+            gx, dw1, db1, dw2 = ops.mlp_head_bwd_fused(x, w1m, b1c, w2v, g, ctx.act)
+            db2 = g.sum().reshape(ctx.shapes[3]) if need_b2 else None
+            return (gx if need_x else None, dw1.reshape(ctx.shapes[0]) if need_w1 else None,
+                    db1.reshape(ctx.shapes[1]) if (need_b1 and b1c is not None) else None,
+                    dw2.reshape(ctx.shapes[2]) if need_w2 else None, db2, None)
         res = ops.mlp_head_bwd(x, w1m, b1c, w2v, g, ctx.act, want_gz=need_w1 or need_b1)
         if res is None:
             raise RuntimeError("mlp_head backward: shape lost its tensor-core kernel between forward and backward")

@@ -506,10 +506,45 @@ def test_tensor_core_mlp_head(case):
     n0 = ops.tensor_core_launches()
     out = P.mlp_head(x, w1, b1, w2, b2, act)
     gs = torch.autograd.grad(out, [x, w1, b1, w2, b2], gout)
-    assert ops.tensor_core_launches() - n0 >= 3, "fused tensor-core head did not run"
+    assert ops.tensor_core_launches() - n0 >= 2, "fused tensor-core head did not run"
     assert rel(out, ref) < TOL
     for name, a, b in zip(("dx", "dw1", "db1", "dw2", "db2"), gs, gref):
         assert rel(a, b) < 2e-5, (name, rel(a, b))
+
+
+@pytest.mark.parametrize("case", [(2, 32, 256, (128, 128), "gelu", False), (9, 32, 256, (128, 128), "gelu", True),
+                                  (3, 20, 200, (16, 24), "gelu", False), (1, 8, 16, (16, 8), "tanh", False),
+                                  (2, 16, 128, (8, 16, 4), "relu", True), (5, 32, 128, (64, 64), "gelu", False)], ids=str)
+def test_head_backward_one_kernel(case):
+    """tc_head_bwd.cu: gx, dW1, db1, dw2 of the Ci -> hidden -> act -> 1 head from ONE kernel (the hidden-channel gradient never
+    reaches memory), vs float64 autograd; optional act'(dz) factor on gx; one / several tiles per CTA; padded channels / hidden."""
+    from pde_policylearning_b200 import ops
+    B, ci, hid, grid, act, with_dact = case
+    dev = _dev()
+    torch.manual_seed(8)
+    nd = len(grid)
+    assert ops.mlp_head_bwd_fused_supported(ci, hid, math.prod(grid))
+    x = torch.randn(B, ci, *grid, device=dev)
+    w1 = torch.randn(hid, ci, device=dev) * 0.3
+    b1 = torch.randn(hid, device=dev)
+    w2 = torch.randn(hid, device=dev) * 0.3
+    g = torch.randn(B, 1, *grid, device=dev)
+    dz = torch.randn(B, ci, *grid, device=dev) if with_dact else None
+    f = {"gelu": torch.nn.functional.gelu, "relu": torch.relu, "tanh": torch.tanh}[act]
+    xd, w1d, b1d, w2d = (t.double().requires_grad_(True) for t in (x, w1, b1, w2))
+    h = f(torch.einsum("ji,bi...->bj...", w1d, xd) + b1d.reshape((1, hid) + (1,) * nd))
+    ref = torch.einsum("j,bj...->b...", w2d, h).unsqueeze(1)
+    gx64, dw164, db164, dw264 = torch.autograd.grad(ref, [xd, w1d, b1d, w2d], g.double())
+    if with_dact:
+        zd = dz.double().requires_grad_(True)
+        gx64 = gx64 * torch.autograd.grad(torch.nn.functional.gelu(zd).sum(), zd)[0]
+    n0 = ops.tensor_core_launches()
+    gx, dw1, db1, dw2 = ops.mlp_head_bwd_fused(x, w1, b1, w2, g, act, dact_z=dz, dact="gelu" if with_dact else None)
+    assert ops.tensor_core_launches() == n0 + 1
+    errs = dict(gx=rel(gx, gx64), dw1=rel(dw1, dw164), db1=rel(db1, db164), dw2=rel(dw2, dw264))
+    print("head backward (one kernel)", case, {k: f"{v:.2e}" for k, v in errs.items()})
+    for k, v in errs.items():
+        assert v < 2e-5, (k, v)
 
 
 # --------------------------------------------------------------------------------------------

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/b2no.h but not exported"
     assert set(_lib.EXPORTS) == declared
-    assert _lib.lib().b2no_version() == 4
+    assert _lib.lib().b2no_version() == 5
     assert b"bad argument" in _lib.lib().b2no_error_string(-1)
 
 
