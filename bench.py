@@ -245,7 +245,7 @@ def kernel_probes(dev, hbm_peak_gbs, tf32_peak_tflops):
 
     def head_bwd():
         i = nxt()
-        ops.mlp_head_bwd(xs[i], w1, b1, w2, g1[i], "gelu", want_gz=True)
+        ops.mlp_head_bwd_fused(xs[i], w1, b1, w2, g1[i], "gelu")
 
     bx = B * C * N * N * 4
     K = plan.modes
@@ -256,13 +256,13 @@ def kernel_probes(dev, hbm_peak_gbs, tf32_peak_tflops):
         dict(kernel="dft_inverse adjoint + W^T g, times GELU'(z) (k_inv_h + k_pw_tc<3>)", fn=inv_dact, bound="hbm", bytes=3 * bx + B * C * K * 8, n=2),
         dict(kernel="dft_inverse + bias + 1x1 skip + GELU, z saved (k_inv_h + k_pw_tc<2>)", fn=inv_fused_gelu, bound="hbm",
              bytes=3 * bx + B * C * K * 8, n=2),
-        dict(kernel="1x1 weight gradient (k_wgrad_tc + reduce)", fn=wgrad, bound="hbm", bytes=2 * bx, n=4),
+        dict(kernel="1x1 weight gradient (k_wgrad_tc + reduce)", fn=wgrad, bound="hbm", bytes=2 * bx, n=5),
         dict(kernel="projection head forward (k_mlp_tc<fwd>)", fn=head_fwd, bound="tensor", bytes=bx + px * 4,
              flops=2.0 * px * (C * H + H), n=1),
-        # algorithmic bytes: read x, read g, write gx -- the 256-wide hidden tensor (and its gradient gz) is NOT
-        # algorithmic traffic ("the 256-wide hidden never touches HBM")
-        dict(kernel="projection head backward (k_mlp_tc<bwd>)", fn=head_bwd, bound="tensor",
-             bytes=2 * bx + px * 4, flops=2.0 * px * (2 * C * H + H), n=1),
+        # algorithmic bytes: read x, read g, write gx -- the 256-wide hidden tensor and its gradient never touch HBM
+        # (SURVEY 8d); flops: z1 recompute + gx + dW1 (three C x H products per pixel) + dw2
+        dict(kernel="projection head backward, one kernel: gx + dW1 + db1 + dw2 (k_head_bwd)", fn=head_bwd, bound="tensor",
+             bytes=2 * bx + px * 4, flops=2.0 * px * (3 * C * H + H), n=1),
     ]
     # flops of the SpectralConv stages (DFT-as-GEMM model of SURVEY 8d), so that the same formula applies to every row
     fl_w = 2.0 * B * C * N * N * 2 * (MODES // 2)               # last-dim real -> complex stage

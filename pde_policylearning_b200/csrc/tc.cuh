@@ -58,8 +58,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #endif
   return ok != 0;
 }
+// -DB2NO_MBAR_SLEEP_NS=n: back off n ns after a failed poll (fewer try_wait requests in the shared-memory pipe)
+#ifndef B2NO_MBAR_SLEEP_NS
+#define B2NO_MBAR_SLEEP_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
+#if B2NO_MBAR_SLEEP_NS > 0
+    __nanosleep(B2NO_MBAR_SLEEP_NS);
+#endif
   }
 }
 

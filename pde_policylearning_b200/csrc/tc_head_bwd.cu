@@ -19,8 +19,8 @@
 // Everything is single buffered (TMEM: W1 4 NB C + D1 64 + F 128 + D3 2 NB C + D2 2C = 512 columns at C = 32, H = 256;
 // shared memory 222 KB): the tensor pipe is the bound (~2400 cycles per step against ~1500 of epilogue math), so the
 // epilogue warps wait for the pipe, not the other way round.
-// Warp roles: 0 TMA producer, 1 MMA issuer, 2-5 X converter (thread = pixel), 6-21 epilogue (4 lane quadrants x 4 column
-// parts of 16 pixels).
+// Warp roles: 0 TMA producer, 1 MMA issuer, 2-5 X converter (thread = pixel) + gx epilogue (D2 -> global), 6-21 epilogue
+// (4 lane quadrants x 4 column parts of 16 pixels).
 #include <string.h>
 
 #include "common.cuh"
@@ -42,6 +42,7 @@ struct HeadBwd {
   const float* w1; const float* b1; const float* w2; const float* g; const float* dz;
   float* gx; float* partial;
   int nsum;                                      // floats per partial row: H*Ci + 2H
+  int skip;                                      // ablation mask (B2NO_HB_SKIP, timing experiments only): 1 G1, 2 G3, 4 G2, 8 math, 16 gx stores, 32 Fs stores, 64 F TMEM stores
 };
 
 // -DB2NO_HB_STAMPS: CTA 0 records clock64() at the hand-over points of its first 64 steps (scripts/hb_stamps.py)
@@ -55,6 +56,19 @@ __device__ long long* g_hb_stamps = nullptr;
 #else
 #define HB_STAMP(role, idx, ev) do { } while (0)
 #endif
+
+// act'(z) of the layer below, out of line: the switch over the activations would otherwise be unrolled 32 times
+__device__ __noinline__ float hb_act_grad(float z, int act) { return b2no_act_grad(z, act); }
+
+// one arrival per warp: every lane has fenced its own writes before the call
+__device__ __forceinline__ void warp_arrive(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
+__device__ __forceinline__ void warp_arrive2(uint64_t* bar_a, uint64_t* bar_b) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) { mbar_arrive(bar_a); mbar_arrive(bar_b); }
+}
 
 struct HbLayout { uint32_t fs, fs_img, wt, xt, xt_img, xk, raw, g, bars, total; };
 
@@ -74,12 +88,13 @@ __host__ __device__ inline HbLayout hb_layout(int Cq, int Hp) {
 
 __host__ __device__ inline uint32_t hb_tmem_cols(int Cq, int NB) { return (uint32_t)(4 * NB * Cq + 192 + 2 * Cq); }
 
-template <bool GELU>
+template <bool GELU, int CQ>
 __global__ void __launch_bounds__(kHbThreads, 1)
 k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int Cq = p.Cq, NB = p.NB, NS = 2 * p.NB, Hp = p.Hp;
+  constexpr int Cq = CQ;                     // channels rounded up to 16 (compile time: the MMA issue loops unroll)
+  const int NB = p.NB, NS = 2 * p.NB, Hp = p.Hp;
   const HbLayout L = hb_layout(Cq, Hp);
   uint64_t* bars = (uint64_t*)(smem + L.bars);
   uint64_t* raw_full = bars + 0;  uint64_t* raw_empty = bars + 1;
@@ -103,12 +118,14 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
     *(float*)(smem + L.wt + kmajor_off(Cq + c, j, Hp)) = tf32_rna(w - hi);
   }
   if (tid == 0) {
-    mbar_init(raw_full, 1);  mbar_init(raw_empty, 128);
-    mbar_init(xt_full, 128); mbar_init(xt_empty, 1);
-    mbar_init(xk_full, 128); mbar_init(xk_empty, 1);
-    mbar_init(d1_full, 1);   mbar_init(d1_empty, kHbEpiThreads);
-    mbar_init(f_full, kHbEpiThreads); mbar_init(f_empty, 1);
-    mbar_init(d2_full, 1);   mbar_init(d2_empty, kHbEpiThreads);
+    // consumer-side barriers count WARPS: every lane fences its own writes, the warp converges (__syncwarp), one lane
+    // arrives -- 512 per-thread arrivals on one mbarrier word serialise in the shared-memory atomic unit
+    mbar_init(raw_full, 1);  mbar_init(raw_empty, 4);
+    mbar_init(xt_full, 4);   mbar_init(xt_empty, 1);
+    mbar_init(xk_full, 4);   mbar_init(xk_empty, 1);
+    mbar_init(d1_full, 1);   mbar_init(d1_empty, kHbEpiThreads / 32);
+    mbar_init(f_full, kHbEpiThreads / 32); mbar_init(f_empty, 1);
+    mbar_init(d2_full, 1);   mbar_init(d2_empty, 4);
     mbar_init(done, 1);
     fence_barrier_init();
   }
@@ -174,7 +191,7 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
     const uint64_t d_fsh = smem_desc(sbase + L.fs, kHbLbo, kHbSbo, LAYOUT_NONE);
     const uint64_t d_fsl = smem_desc(sbase + L.fs + L.fs_img, kHbLbo, kHbSbo, LAYOUT_NONE);
     const uint64_t d_wt = smem_desc(sbase + L.wt, 128, (uint32_t)(Hp / 4) * 128, LAYOUT_NONE);
-    const int k1 = Cq / 8;
+    constexpr int k1 = Cq / 8;
     const bool lo_pass = p.npass >= 3;
     // G3 + G2 of step pn (tile index pit of this CTA, step ps inside the tile)
     auto g3g2 = [&](long pn, int pit, int ps) {
@@ -187,9 +204,10 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
         const uint32_t d3 = t_d3 + (uint32_t)(b * 2 * Cq);
         const uint64_t dxk = d_xk + (uint64_t)(q * 16 * (kHbLbo / 16));        // 64 px = 16 K-chunks of 4
         const uint32_t first = (pit == 0 && q == 0) ? 0u : 1u;
+        if (!(p.skip & 2))
 #pragma unroll
         for (int k = 0; k < 8; k++) mma_tf32_ts(d3, t_f + 8 * k, dxk + (uint64_t)(k * (2 * kHbLbo / 16)), id_n2, (k > 0) ? 1u : first);
-        if (lo_pass) {
+        if (lo_pass && !(p.skip & 2)) {
 #pragma unroll
           for (int k = 0; k < 8; k++) mma_tf32_ts(d3, t_f + 64 + 8 * k, dxk + (uint64_t)(k * (2 * kHbLbo / 16)), id_n1, 1u);
         }
@@ -204,10 +222,11 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
       HB_STAMP(0, pn, 4);
       if (elect_one()) {
         const uint64_t dw = d_wt + (uint64_t)(b * 32 * (128 / 16));             // 128 j = 32 K-chunks of 4
+        if (!(p.skip & 4))
 #pragma unroll
         for (int k = 0; k < 16; k++)
           mma_tf32_ss(t_d2, d_fsh + (uint64_t)(k * (2 * kHbLbo / 16)), dw + (uint64_t)(k * 16), id_g2h, (b > 0 || k > 0) ? 1u : 0u);
-        if (lo_pass) {
+        if (lo_pass && !(p.skip & 4)) {
 #pragma unroll
           for (int k = 0; k < 16; k++)
             mma_tf32_ss(t_d2, d_fsl + (uint64_t)(k * (2 * kHbLbo / 16)), dw + (uint64_t)(k * 16), id_g2l, 1u);
@@ -233,10 +252,10 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
           const uint64_t qoff = (uint64_t)(q * 8 * (sbo_xt / 16));               // 64 px rows = 8 row groups
           uint32_t acc = 0;
           _Pragma("unroll") for (int pass = 0; pass < 3; pass++) {
-            if (pass >= p.npass) break;
+            if (pass >= p.npass || (p.skip & 1)) break;
             const uint32_t a = t_w + (uint32_t)(b * 2 * Cq) + (pass == 1 ? (uint32_t)Cq : 0u);
             const uint64_t dx = (pass == 2 ? d_xtl : d_xth) + qoff;
-            for (int k = 0; k < k1; k++) { mma_tf32_ts(t_d1, a + 8 * k, dx + (uint64_t)(k * 16), id_g1, acc); acc = 1; }
+            _Pragma("unroll") for (int k = 0; k < k1; k++) { mma_tf32_ts(t_d1, a + 8 * k, dx + (uint64_t)(k * 16), id_g1, acc); acc = 1; }
           }
           mma_commit(d1_full);
           if (s == NS - 1) mma_commit(xt_empty);
@@ -259,6 +278,44 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
     const uint32_t sx = sb + L.raw + (uint32_t)m * 4;
     const uint32_t xt_row = sb + L.xt + (uint32_t)(m >> 3) * sbo_xt + (uint32_t)(m & 7) * 16;
     const uint32_t xk_col = sb + L.xk + (uint32_t)(m >> 2) * kHbLbo + (uint32_t)(m & 3) * 4;
+    // gx epilogue of a finished pixel chunk (these warps have the slack; the stores stay off the F hand-over chain).  D2 comes
+    // from M = 64 MMAs: pixel m of the chunk lives in TMEM lane 32 (m / 16) + m % 16 (lanes 0..15 of every quadrant);
+    // columns [0,Cq) + [Cq,2Cq) = channels
+    const int quad = warp & 3;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    auto gx_epilogue = [&](long qc, long tile_of, int q) {
+      mbar_wait(d2_full, (uint32_t)qc & 1u);
+      tc_fence_after();
+      float r[Cq];
+#pragma unroll
+      for (int c0 = 0; c0 < Cq; c0 += 16) {
+        float a[16], l[16];
+        tmem_ld16(t_d2 + lane_base + (uint32_t)c0, a);
+        tmem_ld16(t_d2 + lane_base + (uint32_t)(Cq + c0), l);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; i++) r[c0 + i] = a[i] + l[i];
+      }
+      tc_fence_before();
+      warp_arrive(d2_empty);
+      if (lane < 16 && !(p.skip & 16)) {
+        const int bimg = (int)(tile_of / p.tiles_per_img);
+        const long px = (tile_of - (long)bimg * p.tiles_per_img) * 128 + q * 64 + quad * 16 + lane;
+        const size_t o0 = (size_t)bimg * p.Ci * p.P + (size_t)px;
+        float* gp = p.gx + o0;
+        if (p.dz) {
+          const float* zp = p.dz + o0;
+#pragma unroll
+          for (int c = 0; c < Cq; c++)
+            if (c < p.Ci) gp[(size_t)c * p.P] = r[c] * hb_act_grad(__ldg(zp + (size_t)c * p.P), p.dact);
+        } else {
+#pragma unroll
+          for (int c = 0; c < Cq; c++)
+            if (c < p.Ci) gp[(size_t)c * p.P] = r[c];
+        }
+      }
+    };
+    const int cpt = NS / NB;                                                    // pixel chunks per tile (2)
     int it = 0;
     for (long tile = t_first; tile < t_end; tile++, it++) {
       mbar_wait(raw_full, (uint32_t)it & 1u);
@@ -280,7 +337,7 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
       }
       fence_proxy_async();
       if (warp == 2) HB_STAMP(2, it, 2);
-      mbar_arrive(xt_full);
+      warp_arrive(xt_full);
       mbar_wait(xk_empty, ((uint32_t)it & 1u) ^ 1u);
       if (warp == 2) HB_STAMP(2, it, 3);
       for (int c0 = 0; c0 < Cq; c0 += 8) {
@@ -294,11 +351,13 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
           sts_f32(gl + (uint32_t)u * 16u, tf32_lo(v[u]));
         }
       }
-      mbar_arrive(raw_empty);
       fence_proxy_async();
       if (warp == 2) HB_STAMP(2, it, 4);
-      mbar_arrive(xk_full);
+      warp_arrive2(raw_empty, xk_full);
+      if (it > 0) gx_epilogue((long)it * cpt - 1, tile - 1, cpt - 1);           // closed by the last step of the previous tile
+      gx_epilogue((long)it * cpt, tile, 0);
     }
+    if (it > 0) gx_epilogue((long)it * cpt - 1, t_end - 1, cpt - 1);
   } else {
     // ===================== epilogue: 4 lane quadrants (hidden units) x 4 column parts (16 pixels of the chunk) =====================
     const int part = (warp - 6) >> 2;
@@ -316,41 +375,9 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
       dsa[b] = make_float2(0.f, 0.f);
     }
     const uint32_t fs_base = smem_u32(smem) + L.fs + (uint32_t)(2 * part) * kHbSbo + (uint32_t)(jl >> 2) * kHbLbo + (uint32_t)(jl & 3) * 4;
-    // gx epilogue of a finished pixel chunk.  D2 comes from M = 64 MMAs: pixel m of the chunk lives in TMEM lane
-    // 32 (m / 16) + m % 16 (lanes 0..15 of every quadrant); columns [0,Cq) + [Cq,2Cq) = channels
-    auto gx_epilogue = [&](long qc, int bimg, long pxb) {
-      mbar_wait(d2_full, (uint32_t)qc & 1u);
-      tc_fence_after();
-      float a[8], l[8];
-      const bool live = 8 * part < Cq;
-      if (live) {
-        tmem_ld8(t_d2 + lane_base + (uint32_t)(8 * part), a);
-        tmem_ld8(t_d2 + lane_base + (uint32_t)(Cq + 8 * part), l);
-        tmem_ld_wait();
-      }
-      tc_fence_before();
-      mbar_arrive(d2_empty);
-      if (live && lane < 16) {
-        const long px = pxb + quad * 16 + lane;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const int c = 8 * part + i;
-          if (c < p.Ci) {
-            const size_t o = ((size_t)bimg * p.Ci + c) * p.P + px;
-            float r = a[i] + l[i];
-            if (p.dz) r *= b2no_act_grad(__ldg(p.dz + o), p.dact);
-            p.gx[o] = r;
-          }
-        }
-      }
-    };
     int it = 0;
     long n = 0;
-    int prev_b = 0;
-    long prev_px = 0;
     for (long tile = t_first; tile < t_end; tile++, it++) {
-      const int bimg = (int)(tile / p.tiles_per_img);
-      const long px0 = (tile - (long)bimg * p.tiles_per_img) * 128;
       const uint32_t gs = smem_u32(smem) + L.g + (uint32_t)(it % 3) * 512u;
       for (int s = 0; s < NS; s++, n++) {
         const int q = s / NB, b = s - q * NB;
@@ -363,11 +390,12 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
         for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(gv + i) = lds_v4(gs + (uint32_t)(q * 64 + part * 16 + i) * 4u);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(d1_empty);
+        warp_arrive(d1_empty);
         if (warp == 6) HB_STAMP(1, n, 1);
         const float b1j = b == 0 ? b1r[0] : b1r[1], w2j = b == 0 ? w2r[0] : w2r[1];
         float2 dw2v = b == 0 ? dw2a[0] : dw2a[1], dsv = b == 0 ? dsa[0] : dsa[1];
-        if (GELU) {
+        if (p.skip & 8) {
+        } else if (GELU) {
           float2* v2 = reinterpret_cast<float2*>(v);
           const float2* g2 = reinterpret_cast<const float2*>(gv);
           const float2 bb = b2no_f2(b1j), ww = b2no_f2(w2j);
@@ -396,16 +424,17 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
         mbar_wait(f_empty, ((uint32_t)n & 1u) ^ 1u);
         tc_fence_after();
         if (warp == 6) HB_STAMP(1, n, 3);
-        tmem_st16(t_f + lane_base + (uint32_t)(16 * part), v);
+        if (!(p.skip & 64)) tmem_st16(t_f + lane_base + (uint32_t)(16 * part), v);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
           float fl[8];
 #pragma unroll
           for (int i = 0; i < 8; i++) fl[i] = v[8 * h + i] - tf32_trunc(v[8 * h + i]);     // exact; the tensor core reads its top 19 bits
-          tmem_st8(t_f + lane_base + 64u + (uint32_t)(16 * part + 8 * h), fl);
+          if (!(p.skip & 64)) tmem_st8(t_f + lane_base + 64u + (uint32_t)(16 * part + 8 * h), fl);
 #pragma unroll
           for (int i = 0; i < 8; i++) {
             const uint32_t off = (uint32_t)h * kHbSbo + (uint32_t)i * 16;
+            if (p.skip & 32) continue;
             sts_f32(fs_base + off, v[8 * h + i]);
             sts_f32(fs_base + L.fs_img + off, fl[i]);
           }
@@ -414,14 +443,10 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
         fence_proxy_async();
         tc_fence_before();
         if (warp == 6) HB_STAMP(1, n, 4);
-        mbar_arrive(f_full);
-        // the step before closed a pixel chunk when this one opens a new one
-        if (b == 0 && n > 0) gx_epilogue((long)it * 2 + q - 1, prev_b, prev_px);
-        if (b == NB - 1) { prev_b = bimg; prev_px = px0 + q * 64; }
+        warp_arrive(f_full);
         if (warp == 6) HB_STAMP(1, n, 5);
       }
     }
-    if (n > 0) gx_epilogue((long)it * 2 - 1, prev_b, prev_px);
     // ---- read-out: dW1 from D3, dw2 / db1 from the register sums (column parts combined through shared memory) ----
     mbar_wait(done, 0);
     tc_fence_after();
@@ -545,6 +570,8 @@ extern "C" int b2no_mlp_head_bwd_fused(const float* x, const float* w1, const fl
   p.tiles_per_img = (int)(pixels / 128);
   p.tiles = (long)batch * p.tiles_per_img;
   p.nsum = hidden * ci + 2 * hidden;
+  B2NO_ENV_ONCE(hb_skip, "B2NO_HB_SKIP", 0);
+  p.skip = hb_skip;
   long grid = p.tiles < b2no_sm_count() ? p.tiles : b2no_sm_count();
   p.tiles_per_cta = (p.tiles + grid - 1) / grid;
   grid = (p.tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
@@ -554,13 +581,15 @@ extern "C" int b2no_mlp_head_bwd_fused(const float* x, const float* w1, const fl
   uint64_t str[3] = {4, (uint64_t)pixels * 4, (uint64_t)pixels * 4 * ci};
   uint32_t box[3] = {128, (uint32_t)p.Cq, 1};
   if (make_tmap_f32(&tmx, x, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return B2NO_E_UNSUPPORTED;
-  if (act == B2NO_ACT_GELU) {
-    B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_head_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    k_head_bwd<true><<<(unsigned)grid, kHbThreads, L.total, st>>>(tmx, p);
-  } else {
-    B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_head_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    k_head_bwd<false><<<(unsigned)grid, kHbThreads, L.total, st>>>(tmx, p);
-  }
+#define HB_LAUNCH(G, C)                                                                                                   \
+  do {                                                                                                                   \
+    B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_head_bwd<G, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total)); \
+    k_head_bwd<G, C><<<(unsigned)grid, kHbThreads, L.total, st>>>(tmx, p);                                              \
+  } while (0)
+  const bool gelu = act == B2NO_ACT_GELU;
+  if (p.Cq == 32) { if (gelu) HB_LAUNCH(true, 32); else HB_LAUNCH(false, 32); }
+  else { if (gelu) HB_LAUNCH(true, 16); else HB_LAUNCH(false, 16); }
+#undef HB_LAUNCH
   B2NO_LAUNCH_CHECK();
   b2no_tc_count_launch();
   k_hb_sum<<<(p.nsum + 31) / 32, 256, 0, st>>>(partial, grads, (int)grid, p.nsum);

@@ -25,7 +25,7 @@ torch.cuda.synchronize()
 s = buf.cpu().view(3, 64, 8)
 t0 = int(s[s > 0].min())
 names = [["d1_empty ok", "G1 issued", "f_full ok", "G3 issued", "d2_empty ok", "G2 issued"],
-         ["d1_full ok", "D1 read", "math done", "f_empty ok", "F written", "step end"],
+         ["d1_full ok", "D1 read", "math done", "f_empty ok", "F written", "step end", "[gx: d2_full ok", "D2 read]"],
          ["raw_full ok", "xt_empty ok", "XT written", "xk_empty ok", "XK written"]]
 for role, title in enumerate(["MMA issuer", "epilogue warp 6", "converter warp 2"]):
     print("==", title, "(cycles since first stamp)")
