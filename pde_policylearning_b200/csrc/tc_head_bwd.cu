@@ -38,7 +38,8 @@ constexpr uint32_t kHbSbo = 32 * kHbLbo;         // 128 K elements per 8-row gro
 struct HeadBwd {
   int B, Ci, Cq, H, Hp, NB, act, dact, npass;
   int tiles_per_img;
-  long tiles, tiles_per_cta, P;
+  int tiles, tiles_per_cta;                       // 128-pixel tiles (checked < 2^30 on the host: no 64-bit divisions in the kernel)
+  long P;
   const float* w1; const float* b1; const float* w2; const float* g; const float* dz;
   float* gx; float* partial;
   int nsum;                                      // floats per partial row: H*Ci + 2H
@@ -163,19 +164,19 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
   __syncthreads();
   tc_fence_after();
 
-  const long t_first = (long)blockIdx.x * p.tiles_per_cta;
-  const long t_end = t_first + p.tiles_per_cta < p.tiles ? t_first + p.tiles_per_cta : p.tiles;
+  const int t_first = (int)blockIdx.x * p.tiles_per_cta;
+  const int t_end = t_first + p.tiles_per_cta < p.tiles ? t_first + p.tiles_per_cta : p.tiles;
   const uint32_t sbo_xt = (uint32_t)(Cq / 4) * 128;
 
   if (warp == 0) {
     // ===================== TMA producer: x tile [Cq x 128 px] and the g tile (512 B) =====================
     if (lane == 0) {
       int it = 0;
-      for (long tile = t_first; tile < t_end; tile++, it++) {
+      for (int tile = t_first; tile < t_end; tile++, it++) {
         mbar_wait(raw_empty, ((uint32_t)it & 1u) ^ 1u);
         mbar_arrive_expect_tx(raw_full, (uint32_t)Cq * 512u + 512u);
-        const int b = (int)(tile / p.tiles_per_img);
-        const int px0 = (int)(tile - (long)b * p.tiles_per_img) * 128;
+        const int b = tile / p.tiles_per_img;
+        const int px0 = (tile - b * p.tiles_per_img) * 128;
         tma_load_3d(smem + L.raw, &tmx, raw_full, px0, 0, b);
         bulk_load(smem + L.g + (uint32_t)(it % 3) * 512u, p.g + (size_t)b * p.P + px0, 512u, raw_full);
       }
@@ -239,7 +240,7 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
       HB_STAMP(0, pn, 5);
     };
     // software pipeline over the steps of this CTA: G1 of step n is issued before G3 / G2 of step n - 1 (one call site each)
-    const long nsteps = (t_end - t_first) * NS;
+    const long nsteps = (long)(t_end - t_first) * NS;
     int it = 0, s = 0;
     for (long n = 0; n <= nsteps; n++) {
       if (n < nsteps) {
@@ -283,7 +284,7 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
     // columns [0,Cq) + [Cq,2Cq) = channels
     const int quad = warp & 3;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    auto gx_epilogue = [&](long qc, long tile_of, int q) {
+    auto gx_epilogue = [&](long qc, int tile_of, int q) {
       mbar_wait(d2_full, (uint32_t)qc & 1u);
       tc_fence_after();
       float r[Cq];
@@ -299,8 +300,8 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
       tc_fence_before();
       warp_arrive(d2_empty);
       if (lane < 16 && !(p.skip & 16)) {
-        const int bimg = (int)(tile_of / p.tiles_per_img);
-        const long px = (tile_of - (long)bimg * p.tiles_per_img) * 128 + q * 64 + quad * 16 + lane;
+        const int bimg = tile_of / p.tiles_per_img;
+        const long px = (long)(tile_of - bimg * p.tiles_per_img) * 128 + q * 64 + quad * 16 + lane;
         const size_t o0 = (size_t)bimg * p.Ci * p.P + (size_t)px;
         float* gp = p.gx + o0;
         if (p.dz) {
@@ -317,7 +318,7 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
     };
     const int cpt = NS / NB;                                                    // pixel chunks per tile (2)
     int it = 0;
-    for (long tile = t_first; tile < t_end; tile++, it++) {
+    for (int tile = t_first; tile < t_end; tile++, it++) {
       mbar_wait(raw_full, (uint32_t)it & 1u);
       if (warp == 2) HB_STAMP(2, it, 0);
       mbar_wait(xt_empty, ((uint32_t)it & 1u) ^ 1u);
@@ -377,10 +378,10 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
     const uint32_t fs_base = smem_u32(smem) + L.fs + (uint32_t)(2 * part) * kHbSbo + (uint32_t)(jl >> 2) * kHbLbo + (uint32_t)(jl & 3) * 4;
     int it = 0;
     long n = 0;
-    for (long tile = t_first; tile < t_end; tile++, it++) {
+    for (int tile = t_first; tile < t_end; tile++, it++) {
       const uint32_t gs = smem_u32(smem) + L.g + (uint32_t)(it % 3) * 512u;
       for (int s = 0; s < NS; s++, n++) {
-        const int q = s / NB, b = s - q * NB;
+        const int q = NB == 2 ? (s >> 1) : s, b = NB == 2 ? (s & 1) : 0;
         mbar_wait(d1_full, (uint32_t)n & 1u);
         tc_fence_after();
         if (warp == 6) HB_STAMP(1, n, 0);
@@ -568,11 +569,13 @@ extern "C" int b2no_mlp_head_bwd_fused(const float* x, const float* w1, const fl
   p.w1 = w1; p.b1 = b1; p.w2 = w2; p.g = g; p.gx = gx; p.partial = partial;
   p.P = (long)pixels;
   p.tiles_per_img = (int)(pixels / 128);
-  p.tiles = (long)batch * p.tiles_per_img;
+  const long tiles = (long)batch * p.tiles_per_img;
+  if (tiles >= (1L << 30)) return B2NO_E_UNSUPPORTED;
+  p.tiles = (int)tiles;
   p.nsum = hidden * ci + 2 * hidden;
   B2NO_ENV_ONCE(hb_skip, "B2NO_HB_SKIP", 0);
   p.skip = hb_skip;
-  long grid = p.tiles < b2no_sm_count() ? p.tiles : b2no_sm_count();
+  int grid = p.tiles < b2no_sm_count() ? p.tiles : b2no_sm_count();
   p.tiles_per_cta = (p.tiles + grid - 1) / grid;
   grid = (p.tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
   const HbLayout L = hb_layout(p.Cq, p.Hp);
