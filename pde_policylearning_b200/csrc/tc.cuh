@@ -81,6 +81,12 @@ __device__ __forceinline__ float lds_f32(uint32_t a) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
   return v;
 }
+// read-only tables written once before the roles start (not volatile: the compiler may schedule / merge these loads)
+__device__ __forceinline__ float4 lds_v4_ro(uint32_t a) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ float4 lds_v4(uint32_t a) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");

@@ -36,6 +36,8 @@ def two(i):
     ops.pw_wgrad(gz, xs[i % 3], need_bias=True)
 
 
+b2 = torch.randn(1, device=dev)
+print("head forward (k_mlp_tc<fwd, direct>): %.1f us" % timeit(lambda i: ops.mlp_head_fwd(xs[i % 3], w1, b1, w2, b2, "gelu")))
 print("one-kernel head backward: %.1f us" % timeit(fused))
 print("round-1 path (k_mlp_tc<bwd> + k_wgrad_tc): %.1f us" % timeit(two))
 for mode in ("tf32",):

@@ -201,6 +201,27 @@ def mlp_head_bwd_supported(ci, hidden, pixels):
     return False
 
 
+def mlp_head_bwd_fused_supported(ci, hidden, pixels):
+    return ci <= 32 and hidden <= 256 and pixels % 128 == 0
+
+
+def mlp_head_bwd_fused(x, w1, b1, w2, g, act="gelu", dact_z=None, dact=None):
+    """Definition of b2no_mlp_head_bwd_fused (include/b2no.h): (gx, dW1, db1, dw2) of out = w2 . act(W1 x + b1)."""
+    nd = x.dim() - 2
+    xd, w1d, w2d = (t.detach().to(RD).requires_grad_(True) for t in (x, w1, w2))
+    b1d = (torch.zeros(w1.shape[0], dtype=RD) if b1 is None else b1.detach().to(RD)).requires_grad_(True)
+    with torch.enable_grad():
+        z = torch.einsum("ji,bi...->bj...", w1d, xd) + b1d.reshape((1, -1) + (1,) * nd)
+        y = torch.einsum("j,bj...->b...", w2d, _act(z, act)).unsqueeze(1)
+        gx, dw1, db1, dw2 = torch.autograd.grad(y, [xd, w1d, b1d, w2d], g.to(RD))
+    if dact_z is not None:
+        zz = dact_z.detach().to(RD).requires_grad_(True)
+        with torch.enable_grad():
+            (da,) = torch.autograd.grad(_act(zz, dact).sum(), zz)
+        gx = gx * da
+    return tuple(t.to(torch.float32) for t in (gx, dw1, db1, dw2))
+
+
 def mlp_head_fwd(x, w1, b1, w2, b2, act="gelu"):
     z = torch.einsum("ji,bi...->bj...", w1.to(RD), x.to(RD))
     nd = x.dim() - 2
@@ -284,7 +305,7 @@ def pino_residual_bwd(w, u0, forcing2d, nu, t_interval, du_p, fields, coef, gup)
 
 
 _NAMES = ["pino_residual_supported", "pino_residual_fwd", "pino_residual_bwd", "get_plan", "_require_cuda", "dft_forward", "make_epilogue", "dft_inverse", "pointwise", "mix", "mix_dw",
-          "act_bwd", "pw_wgrad", "mlp_head_bwd_supported", "mlp_head_fwd", "rno_gate_fwd", "rno_gate_bwd", "rno_cell_bwd",
+          "act_bwd", "pw_wgrad", "mlp_head_bwd_supported", "mlp_head_bwd_fused_supported", "mlp_head_bwd_fused", "mlp_head_fwd", "rno_gate_fwd", "rno_gate_bwd", "rno_cell_bwd",
           "rno_reset_bwd", "rel_l2_sums", "rel_l2_finish", "rel_l2_bwd_g"]
 
 

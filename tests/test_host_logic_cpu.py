@@ -108,3 +108,27 @@ def test_pino_family_mirrors_match_reference_fixtures(golden):
         m.load_state_dict(c["state_dict"])
         with torch.no_grad():
             assert rel(m(*c["inputs"]), c["out"]) < 2e-5
+
+
+def test_mlp_head_autograd_node_with_the_one_kernel_backward():
+    """functional.MlpHeadFn: forward through mlp_head_fwd, backward through the one-kernel entry point (gx, dW1, db1, dw2 in
+    one call, db2 = sum g) -- host logic checked against float64 autograd of the reference head (tfno.py:34-38)."""
+    import pde_policylearning_b200.functional as Fn
+    torch.manual_seed(3)
+    B, ci, hid, grid = 2, 5, 12, (8, 16)
+    x = torch.randn(B, ci, *grid, requires_grad=True)
+    w1 = (torch.randn(hid, ci, 1, 1) * 0.4).requires_grad_(True)
+    b1 = torch.randn(hid, requires_grad=True)
+    w2 = (torch.randn(1, hid, 1, 1) * 0.4).requires_grad_(True)
+    b2 = torch.randn(1, requires_grad=True)
+    g = torch.randn(B, 1, *grid)
+    ts = [t.detach().double().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    h = torch.nn.functional.gelu(torch.nn.functional.conv2d(ts[0], ts[1], ts[2]))
+    ref = torch.nn.functional.conv2d(h, ts[3], ts[4])
+    gref = torch.autograd.grad(ref, ts, g.double())
+    with emu.installed():
+        out = Fn.MlpHeadFn.apply(x, w1, b1, w2, b2, "gelu")
+        gs = torch.autograd.grad(out, [x, w1, b1, w2, b2], g)
+    assert rel(out, ref) < 1e-6
+    for a, b in zip(gs, gref):
+        assert a.shape == b.shape and rel(a, b) < 1e-6
