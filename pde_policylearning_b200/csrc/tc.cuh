@@ -245,7 +245,14 @@ __device__ __forceinline__ float tf32_rna(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+// lo = x - trunc(x) is exact in fp32 (it is the low 13 mantissa bits); the tensor core then reads ITS upper 19 bits, i.e.
+// truncates it to 10 mantissa bits: hi + lo carries 21 mantissa bits, error 2^-21 relative to x.  Rounding lo first (cvt.rna,
+// an XU-pipe instruction with a long latency, one per element in every converter loop) would only gain the last half bit.
+#ifdef B2NO_LO_RNA
 __device__ __forceinline__ float tf32_lo(float x) { return tf32_rna(x - tf32_trunc(x)); }
+#else
+__device__ __forceinline__ float tf32_lo(float x) { return x - tf32_trunc(x); }
+#endif
 
 // K-major, no-swizzle ("interleaved") canonical layout for 4-byte elements: core matrix = 8 rows x 16 B.
 // Element (r, k) of an [R x K] operand lives at byte offset

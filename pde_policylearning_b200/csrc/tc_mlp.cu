@@ -29,6 +29,9 @@ constexpr int kNP = 64 / kEW;                  // column parts -> kNP x 4 epilog
 constexpr int kEpiThreads = 128 * kNP;
 constexpr int kThreadsMlp = 192 + kEpiThreads;
 
+// generic activation out of line (the switch would otherwise be unrolled 32 times in the two-group forward)
+__device__ __noinline__ float mlp_act_ool(float z, int act) { return b2no_act(z, act); }
+
 struct MlpTc {
   int B, Ci, Cip, H, Hp, NC, N2, Co2, S, fbufs, mode, act, b1_per_sample, dact, direct;
   int npass;   // 3: 3xTF32, 1: single-pass TF32
@@ -49,7 +52,7 @@ __host__ __device__ inline MlpLayout mlp_layout(const MlpTc& p) {
   L.b1 = o; o += (uint32_t)p.Hp * 4;
   L.w2v = o; o += (uint32_t)p.Hp * 4;
   L.dw2 = o; o += (uint32_t)p.Hp * 4;
-  L.part = o; o += 2 * (kNP - 1) * 128 * 4;
+  L.part = o; o += 2 * 4 * 128 * 4;
   o = (o + 1023u) & ~1023u;
   L.stages = o;
   L.stage_bytes = (uint32_t)p.Cip * 512;
@@ -117,9 +120,12 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
   if (tid == 0) {
     for (int s = 0; s < p.S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 128); }
     mbar_init(x_full, 128); mbar_init(x_empty, 1);
-    for (int a = 0; a < 4; a++) { mbar_init(&acc1_full[a], 1); mbar_init(&acc1_empty[a], kEpiThreads); }
+    // two-group DIRECT forward: a 64-column chunk belongs to one group of 8 epilogue warps (one arrival per warp); the
+    // f_full / f_empty slots serve as "partials of tile parity a written" (16 warps) / "... consumed" (4 converter warps)
+    const bool two_groups = DIRECT && (p.NC & 1) == 0;
+    for (int a = 0; a < 4; a++) { mbar_init(&acc1_full[a], 1); mbar_init(&acc1_empty[a], two_groups ? 8 : kEpiThreads); }
     for (int a = 0; a < 2; a++) {
-      mbar_init(&f_full[a], kEpiThreads); mbar_init(&f_empty[a], 1);
+      mbar_init(&f_full[a], two_groups ? 16 : kEpiThreads); mbar_init(&f_empty[a], two_groups ? 4 : 1);
       mbar_init(&acc2_full[a], 1); mbar_init(&acc2_empty[a], kEpiThreads);
     }
     fence_barrier_init();
@@ -225,6 +231,20 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
     const int quad = warp & 3;
     const int m = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    // two-group DIRECT forward: out[pixel m] of a finished tile = b2 + the four partial sums (2 groups x 2 column halves) the
+    // epilogue warps left in shared memory, added in a fixed order; the store and the wait stay off the epilogue's chain
+    auto direct_combine = [&](int jt, long jtile) {
+      const int a = jt & 1;
+      mbar_wait(&f_full[a], (uint32_t)(jt >> 1) & 1u);
+      const uint32_t pp = smem_u32(smem) + L.part + (uint32_t)(a * 4 * 128 + m) * 4u;
+      float o = p.b2 ? __ldg(p.b2) : 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; q++) o += lds_f32(pp + (uint32_t)q * 512u);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&f_empty[a]);
+      const int b = (int)(jtile / p.tiles_per_img);
+      p.out[(size_t)b * p.P + (jtile - (long)b * p.tiles_per_img) * 128 + m] = o;
+    };
     int it = 0;
     for (long tile = t_first; tile < t_end; tile++, it++) {
       const int s = it % p.S;
@@ -247,7 +267,9 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(x_full);
+      if (DIRECT && (NC & 1) == 0 && it > 0) direct_combine(it - 1, tile - 1);
     }
+    if (DIRECT && (NC & 1) == 0 && it > 0) direct_combine(it - 1, t_end - 1);
   } else {
     // ===================== epilogue: 4 lane quadrants x kNP column parts =====================
     const int part_id = (warp - 6) >> 2;
@@ -257,6 +279,59 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
     const float* sb1 = (const float*)(smem + L.b1);
     const float* sw2 = (const float*)(smem + L.w2v);
     float* sdw2 = (float*)(smem + L.dw2);
+    if (DIRECT && (NC & 1) == 0) {
+      // ---- forward, one output channel, two groups of 8 warps on alternating 64-column chunks: while one group waits for
+      // its accumulator and reads it, the other one keeps the FMA pipe busy with the GELU math (every SMSP holds two warps of
+      // each group).  Each thread owns 32 columns of its group's chunks and sums w2[j] gelu(z1[j]) in fp32 registers.
+      const int sub = (warp - 6) >> 2, grp = sub & 1, half = sub >> 1;
+      const uint32_t s_b1 = smem_u32(smem) + L.b1, s_w2 = smem_u32(smem) + L.w2v;
+      const uint32_t s_part = smem_u32(smem) + L.part + (uint32_t)(sub * 128 + t) * 4u;
+      const long ntot = (t_end - t_first) * (long)NC;
+      int it = 0, c = grp;
+      long tile = t_first;
+      float2 oacc = make_float2(0.f, 0.f);
+      for (long n = grp; n < ntot; n += 2) {
+        const int ab = (int)(n % NA);
+        const int col0 = c * 64 + half * 32;
+        mbar_wait(&acc1_full[ab], (uint32_t)(n / NA) & 1u);
+        tc_fence_after();
+        float v[32];
+        tmem_ld32(t_acc1 + lane_base + 64u * ab + half * 32, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc1_empty[ab]);
+        if (GELU && !p.b1_per_sample) {
+          const float2* v2 = reinterpret_cast<const float2*>(v);
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float4 bq = lds_v4_ro(s_b1 + (uint32_t)(col0 + 4 * j) * 4u), wq = lds_v4_ro(s_w2 + (uint32_t)(col0 + 4 * j) * 4u);
+            oacc = __ffma2_rn(b2no_gelu2(__fadd2_rn(v2[2 * j], make_float2(bq.x, bq.y))), make_float2(wq.x, wq.y), oacc);
+            oacc = __ffma2_rn(b2no_gelu2(__fadd2_rn(v2[2 * j + 1], make_float2(bq.z, bq.w))), make_float2(wq.z, wq.w), oacc);
+          }
+        } else {
+          const int b = (int)(tile / p.tiles_per_img);
+          const float* b1g = p.b1_per_sample ? p.b1 + (size_t)b * p.H : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const float bj = b1g ? __ldg(b1g + min(col0 + j, p.H - 1)) : lds_f32(s_b1 + (uint32_t)(col0 + j) * 4u);
+            oacc.x = fmaf(mlp_act_ool(v[j] + bj, p.act), lds_f32(s_w2 + (uint32_t)(col0 + j) * 4u), oacc.x);
+          }
+        }
+        c += 2;
+        if (c >= NC) {
+          // this group's part of the tile is done: leave the partial sum for the converter warps (buffer of the tile's parity,
+          // free again once they have consumed the tile two back)
+          const int a = it & 1;
+          mbar_wait(&f_empty[a], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+          sts_f32(s_part + (uint32_t)a * 2048u, oacc.x + oacc.y);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&f_full[a]);
+          oacc = make_float2(0.f, 0.f);
+          c = grp; tile++; it++;
+        }
+      }
+    } else {
     int it = 0;
     long n1 = 0;
     for (long tile = t_first; tile < t_end; tile++, it++) {
@@ -417,6 +492,7 @@ k_mlp_tc(const __grid_constant__ CUtensorMap tmx, const MlpTc p) {
       }
       tc_fence_before();
       mbar_arrive(&acc2_empty[a2]);
+    }
     }
   }
   tc_fence_before();

@@ -297,39 +297,38 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
       if (p.Ks) {
         // A' rows arrive as ONE fp32 image (half the bytes k_inv_h writes and this kernel reads); split it in place into
         // the tf32 hi image and the lo image next to it, then make the generic-proxy writes visible to the MMAs
-        float* ah = (float*)(smem + L.stages + (size_t)s * L.stage_bytes + L.ah);
-        float* al = (float*)(smem + L.stages + (size_t)s * L.stage_bytes + L.al);
+        // (explicit shared-space accesses: a generic pointer into the dynamic window compiles to LD.E / ST.E)
+        const uint32_t ah = smem_u32(smem) + L.stages + (uint32_t)s * L.stage_bytes + L.ah;
+        const uint32_t al = smem_u32(smem) + L.stages + (uint32_t)s * L.stage_bytes + L.al;
         for (int i = m * 4; i < p.Ks * p.Np; i += 512) {
-          const float4 v = *reinterpret_cast<const float4*>(ah + i);
+          const float4 v = lds_v4(ah + (uint32_t)i * 4u);
           const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-          *reinterpret_cast<float4*>(ah + i) = h;
-          *reinterpret_cast<float4*>(al + i) = make_float4(tf32_rna(v.x - h.x), tf32_rna(v.y - h.y), tf32_rna(v.z - h.z), tf32_rna(v.w - h.w));
+          sts_v4(ah + (uint32_t)i * 4u, h);
+          sts_v4(al + (uint32_t)i * 4u, make_float4(tf32_rna(v.x - h.x), tf32_rna(v.y - h.y), tf32_rna(v.z - h.z), tf32_rna(v.w - h.w)));
         }
         fence_proxy_async();
       }
       mbar_wait(&a_empty[a], aph ^ 1u);
       tc_fence_after();
-      const float* sx = (const float*)(smem + L.stages + (size_t)s * L.stage_bytes);
+      const uint32_t sx = smem_u32(smem) + L.stages + (uint32_t)s * L.stage_bytes + (uint32_t)m * 4u;
       const uint32_t xa = a_base + (uint32_t)a * a_width + lane_base;
       for (int c0 = 0; c0 < p.C1p; c0 += 8) {
         float hi[8], lo[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          hi[j] = sx[(c0 + j) * 128 + m];
-          lo[j] = tf32_lo(hi[j]);
-        }
+        for (int j = 0; j < 8; j++) hi[j] = lds_f32(sx + (uint32_t)(c0 + j) * 512u);
+#pragma unroll
+        for (int j = 0; j < 8; j++) lo[j] = tf32_lo(hi[j]);
         tmem_st8(xa + c0, hi);
         tmem_st8(xa + p.C1p + c0, lo);
       }
       if (p.C2p) {
-        const float* sx2 = (const float*)((const uint8_t*)sx + L.x2);
+        const uint32_t sx2 = sx + L.x2;
         for (int c0 = 0; c0 < p.C2p; c0 += 8) {
           float hi[8], lo[8];
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            hi[j] = sx2[(c0 + j) * 128 + m];
-            lo[j] = tf32_lo(hi[j]);
-          }
+          for (int j = 0; j < 8; j++) hi[j] = lds_f32(sx2 + (uint32_t)(c0 + j) * 512u);
+#pragma unroll
+          for (int j = 0; j < 8; j++) lo[j] = tf32_lo(hi[j]);
           tmem_st8(xa + 2 * p.C1p + c0, hi);
           tmem_st8(xa + 2 * p.C1p + p.C2p + c0, lo);
         }
@@ -366,7 +365,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int t = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    const float* sbias = (const float*)(smem + L.bias);
+    const uint32_t sbias = smem_u32(smem) + L.bias;
     const bool nostore = (p.debug & 1) != 0;
     // MODE 3: the saved pre-activations of the layer below arrive through the TMA ring (dz tile [Cz x 128 px] in the
     // stage, S tiles ahead of their use); with one pass per tile (Co <= 32) the thread takes its 8 values and releases the
@@ -382,13 +381,13 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
       const long px = (tile - (long)b * p.tiles_per_img) * 128 + t;
       const size_t base = (size_t)b * p.Co * p.P + px;
       const int s = it % p.S;
-      const float* sdz = (const float*)(smem + L.stages + (size_t)s * L.stage_bytes + L.dz);
+      const uint32_t sdz = smem_u32(smem) + L.stages + (uint32_t)s * L.stage_bytes + L.dz + (uint32_t)t * 4u;
       float dcur[kCW];
       if (dz_ring) {
         mbar_wait(&full[s], (uint32_t)(it / p.S) & 1u);
         if (dz_single) {
 #pragma unroll
-          for (int j = 0; j < kCW; j++) dcur[j] = (part * kCW + j < p.Cz) ? sdz[(part * kCW + j) * 128 + t] : 0.f;
+          for (int j = 0; j < kCW; j++) dcur[j] = (part * kCW + j < p.Cz) ? lds_f32(sdz + (uint32_t)(part * kCW + j) * 512u) : 0.f;
           mbar_arrive(&empty[s]);
         }
       }
@@ -415,7 +414,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
           for (int j = 0; j < kCW; j++) {
             if (c0 + j < p.Co) {
               const size_t idx = base + (size_t)(c0 + j) * p.P;
-              const float z = v[j] + sbias[c0 + j] + av[j];
+              const float z = v[j] + lds_f32(sbias + (uint32_t)(c0 + j) * 4u) + av[j];
               if (p.preact) p.preact[idx] = z;
               const float r = fmaf(1.0f - gzv[j], ghv[j], epi_value<0>(z, mv[j], dv[j], p.act, p.dact));
               if (!nostore) p.y[idx] = r;
@@ -429,7 +428,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
               for (int j = 0; j < kCW; j++) dv[j] = dcur[j];
             } else if (dz_ring) {
 #pragma unroll
-              for (int j = 0; j < kCW; j++) dv[j] = (c0 + j < p.Cz) ? sdz[(c0 + j) * 128 + t] : 0.f;
+              for (int j = 0; j < kCW; j++) dv[j] = (c0 + j < p.Cz) ? lds_f32(sdz + (uint32_t)(c0 + j) * 512u) : 0.f;
             } else {
 #pragma unroll
               for (int j = 0; j < kCW; j++) dv[j] = (c0 + j < p.Co) ? __ldg(p.dz + base + (size_t)(c0 + j) * p.P) : 0.f;
@@ -443,7 +442,7 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
           }
           float bv[kCW];
 #pragma unroll
-          for (int j = 0; j < kCW; j += 4) *reinterpret_cast<float4*>(bv + j) = *reinterpret_cast<const float4*>(sbias + c0 + j);
+          for (int j = 0; j < kCW; j += 4) *reinterpret_cast<float4*>(bv + j) = lds_v4_ro(sbias + (uint32_t)(c0 + j) * 4u);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < kCW; j++) v[j] += bv[j];

@@ -1,3 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for m in 0 1 8 9; do echo "B2NO_MLP_SKIP=$m"; B2NO_MLP_SKIP=$m timeout 100 python scripts/hb_time.py 2>&1 | head -1; done | tee gpurun_out/hf_ablate.log
+timeout 300 python -m pytest tests/test_gpu_parity.py -q -x --timeout 60 -k "mlp_head or head_backward or observer or fno2d or pino or rno" 2>&1 | tail -5 | tee gpurun_out/hf_test.log
+timeout 100 python scripts/hb_time.py 2>&1 | tee gpurun_out/hf_time.log
