@@ -188,14 +188,26 @@ __device__ __forceinline__ float2 b2no_gelu2(float2 x) {
   const float2 h = __fmul2_rn(x, b2no_f2(0.5f));
   return __ffma2_rn(h, e, h);
 }
-// gelu(x) and gelu'(x) = Phi(x) + x phi(x) sharing the erf
+// gelu(x) and gelu'(x) = Phi(x) + x phi(x) together.  The derivative needs the Gaussian g = exp(-x^2 / 2) anyway, and with g in
+// hand the normal CDF comes cheaper through Abramowitz-Stegun 7.1.26 than through the rational erf above:
+//     erfc(u) = (a1 t + .. + a5 t^5) exp(-u^2),  t = 1 / (1 + p u),  |error| <= 1.5e-7,   u = |x| / sqrt 2  =>  exp(-u^2) = g
+//     Phi(x) = 1/2 + copysign(1/2 - 1/2 poly(t) g, x)
+// 14 FMA-pipe instructions per PAIR instead of 22 (the backward epilogues are FMA-pipe bound), the same 4 MUFU (2 rcp, 2 ex2).
+// Against float64: gelu 8e-8, gelu' 9e-8 relative L2 on N(0, 1.5) inputs (tests/test_host_cpu.py restates it in float32).
 __device__ __forceinline__ void b2no_gelu2_both(float2 x, float2* val, float2* grad) {
-  const float2 e = b2no_erf2(__fmul2_rn(x, b2no_f2(0.70710678118654752440f)));
-  const float2 h = __fmul2_rn(x, b2no_f2(0.5f));
-  *val = __ffma2_rn(h, e, h);
-  const float2 cdf = __ffma2_rn(e, b2no_f2(0.5f), b2no_f2(0.5f));
-  const float2 t = __fmul2_rn(__fmul2_rn(x, x), b2no_f2(-0.72134752044448170368f));   // -0.5 x^2 log2(e)
-  const float2 g = make_float2(b2no_ex2(t.x), b2no_ex2(t.y));
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 den = __ffma2_rn(ax, b2no_f2(0.23164189f), b2no_f2(1.0f));                 // p / sqrt 2
+  const float2 t = make_float2(b2no_rcp(den.x), b2no_rcp(den.y));
+  float2 q = __ffma2_rn(b2no_f2(1.061405429f), t, b2no_f2(-1.453152027f));
+  q = __ffma2_rn(q, t, b2no_f2(1.421413741f));
+  q = __ffma2_rn(q, t, b2no_f2(-0.284496736f));
+  q = __ffma2_rn(q, t, b2no_f2(0.254829592f));
+  q = __fmul2_rn(q, t);
+  const float2 a = __fmul2_rn(__fmul2_rn(x, x), b2no_f2(-0.72134752044448170368f));       // -0.5 x^2 log2(e)
+  const float2 g = make_float2(b2no_ex2(a.x), b2no_ex2(a.y));
+  const float2 h = __ffma2_rn(__fmul2_rn(q, g), b2no_f2(-0.5f), b2no_f2(0.5f));           // 1/2 erf(|x| / sqrt 2)
+  const float2 cdf = __fadd2_rn(b2no_f2(0.5f), make_float2(copysignf(h.x, x.x), copysignf(h.y, x.y)));
+  *val = __fmul2_rn(x, cdf);
   *grad = __ffma2_rn(__fmul2_rn(x, b2no_f2(0.39894228040143267794f)), g, cdf);
 }
 __device__ __forceinline__ float2 b2no_gelu2_grad(float2 x) {

@@ -154,6 +154,32 @@ def test_fast_erf_coefficients():
     assert np.abs(approx - ref).max() < 6e-7
 
 
+def test_gelu_with_gradient_formulation():
+    """csrc/common.cuh::b2no_gelu2_both (Abramowitz-Stegun 7.1.26 on the Gaussian the derivative needs anyway), restated in
+    numpy float32 with the coefficients read from the source: GELU and GELU' against float64 (F.gelu is the erf form)."""
+    import numpy as np
+    src = open(os.path.join(ROOT, "pde_policylearning_b200", "csrc", "common.cuh")).read()
+    body = src[src.index("void b2no_gelu2_both"):src.index("float2 b2no_gelu2_grad")]
+    nums = [float(t) for t in re.findall(r"b2no_f2\((-?\d+\.\d+)f\)", body)]
+    p, one, a5, a4, a3, a2, a1, c, mh, ph, half, k = [np.float32(v) for v in nums]
+    assert (one, mh, ph, half) == (1.0, -0.5, 0.5, 0.5)
+    f = np.float32
+    x = np.linspace(-12, 12, 400001).astype(f)
+    t = (f(1) / (f(1) + p * np.abs(x))).astype(f)
+    q = a5
+    for a in (a4, a3, a2, a1):
+        q = (q * t + a).astype(f)
+    q = (q * t).astype(f)
+    g = np.exp2(((x * x).astype(f) * c).astype(f)).astype(f)
+    cdf = (half + np.copysign((ph + mh * (q * g).astype(f)).astype(f), x)).astype(f)
+    val, grad = (x * cdf).astype(f), (cdf + (x * k).astype(f) * g).astype(f)
+    x64 = torch.from_numpy(x.astype(np.float64)).requires_grad_(True)
+    ref = torch.nn.functional.gelu(x64)
+    (gref,) = torch.autograd.grad(ref.sum(), x64)
+    assert np.abs(val - ref.detach().numpy()).max() < 6e-7
+    assert np.abs(grad - gref.numpy()).max() < 6e-7
+
+
 def test_pino_residual_matches_reference_fixture_and_oracle(golden):
     """Row a8 (diff_control_env.py:5-41) as DFT-matrix contractions: the residual of the reference's own output equals
     the Du the unmodified reference produced (fixture), and values + gradients equal the torch.fft restatement."""
