@@ -22,7 +22,7 @@
 //   warp 0      TMA producer (X boxes, cp.async.bulk for the A' rows), S-deep mbarrier ring
 //   warp 1      MMA issuer (one lane): tcgen05.mma.kind::tf32 TS form, tcgen05.commit -> mbarriers
 //   warps 2-5   converter: shared memory -> TMEM A operand (double buffered)
-//   warps 6-21  epilogue: all sixteen warps work on each tile (4 lane quadrants x 4 column parts of 8 channels: the
+//   warps 6-21  epilogue: two groups of eight warps on alternate tiles (r2; round 1: all sixteen on each tile, 4 lane quadrants x 4 column parts of 8 channels: the
 //               epilogue is a latency chain -- tcgen05.ld, GELU, 128-byte stores per channel row -- and eight warps
 //               left the issue slots half empty), tcgen05.ld -> bias/act -> coalesced global stores;
 //               two TMEM accumulators so the MMAs of tile i+1 overlap the epilogue of tile i.  MODE 3 fetches the
@@ -37,9 +37,11 @@ using namespace tc;
 
 namespace {
 
-constexpr int kParts = 4;                       // column parts of the epilogue (kParts x 4 warps)
+constexpr int kParts = 2;                       // column parts of one epilogue group (kParts x 4 warps); two groups take alternate tiles
+constexpr int kGroups = 2;
 constexpr int kCW = 8;                          // output channels per epilogue thread per pass
-constexpr int kEpiThreadsPw = 128 * kParts;
+constexpr int kEpiThreadsPw = 128 * kParts * kGroups;
+constexpr int kGroupThreadsPw = 128 * kParts;   // the threads that work on one tile (= arrivals on its barriers)
 constexpr int kThreads = 192 + kEpiThreadsPw;
 
 struct PwTc {
@@ -154,10 +156,10 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
   }
   if (tid == 0) {
     // a stage is free when its MMAs have completed and (dz ring) every epilogue thread has taken its dz values
-    for (int s = 0; s < p.S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1 + ((MODE == 3 && p.Cz) ? kEpiThreadsPw : 0)); }
+    for (int s = 0; s < p.S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1 + ((MODE == 3 && p.Cz) ? kGroupThreadsPw : 0)); }
     for (int a = 0; a < 2; a++) {
       mbar_init(&a_full[a], 128); mbar_init(&a_empty[a], 1);
-      mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], kEpiThreadsPw);
+      mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], kGroupThreadsPw);
     }
     fence_barrier_init();
   }
@@ -360,8 +362,12 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
       mbar_arrive(&a_full[a]);
     }
   } else {
-    // ===================== epilogue: 16 warps per tile = 4 lane quadrants x 4 column parts =====================
-    const int part = (warp - 6) >> 2;
+    // ===================== epilogue: 8 warps per tile = 4 lane quadrants x 2 column parts, two groups =====================
+    // sixteen warps = two groups of eight (4 lane quadrants x 2 column parts); group g owns the tiles with it % 2 == g, i.e. the
+    // accumulator a = g: while one group is in its stores, the other reads its accumulator and computes (every SMSP holds two
+    // warps of each group).  Round 1 had all sixteen warps on every tile, in the same phase at the same time.
+    const int sub = (warp - 6) >> 2, grp = sub & 1;
+    const int part = sub >> 1;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int t = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
@@ -373,8 +379,8 @@ k_pw_tc(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtenso
     // them with plain loads left only one tile of dz in flight per SM: 133 us, 3.0 TB/s.)
     const bool dz_ring = MODE == 3 && p.Cz > 0;
     const bool dz_single = p.Co <= kCW * kParts;
-    int it = 0;
-    for (long tile = t_first; tile < t_end; tile++, it++) {
+    int it = grp;
+    for (long tile = t_first + grp; tile < t_end; tile += kGroups, it += kGroups) {
       const int a = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
       const int b = (int)(tile / p.tiles_per_img);
@@ -686,7 +692,7 @@ int b2no_tc_pointwise(const b2no_plan* plan, int which, const float* spec, float
   // dz through the TMA ring: enabled for the single-pass case (Co <= 32: every epilogue thread takes its 8 values and
   // releases the stage at once), which is what the parity tests and the bench exercise; wider layers keep the per-thread
   // loads until the multi-pass variant of the ring has its own GPU test
-  if (mode == 3 && (((uintptr_t)p.dz & 15) == 0) && channels <= kCW * kParts) p.Cz = b2no_round_up(channels, 8);
+  if (mode == 3 && (((uintptr_t)p.dz & 15) == 0) && channels <= kCW * kParts * kGroups) p.Cz = b2no_round_up(channels, 8);
   // shared-memory budget -> number of stages
   int dev = 0, max_smem = 0;
   B2NO_CHECK_CUDA(cudaGetDevice(&dev));
