@@ -318,6 +318,135 @@ static int run_cmat(const float2* in, float2* out, const float2* T, long outer, 
 }
 
 // =============================================================================================
+// k_fwd_plane32: both stages of the 2-D forward transform for SMALL planes (H, W <= 32: the RNO 32 x 32 grid), one WARP per
+// plane, nothing but the plane read and the kept modes written.
+//   stage 1 (lane = row h, the row of x in 32 registers):  A[h, ky] = sum_w x[h, w] (T[2ky, w] + i T[2ky+1, w])
+//   stage 2 (lane = kept row kx):                          Xh[kx, ky] = sum_h M[h, kx] A[h, ky]
+// Packed fp32x2 arithmetic (exact fp32, no tensor cores): stage 1 one FFMA2 per (w, ky), stage 2 two per (h, ky) with
+// separate accumulators for the Re M and Im M products (no operand swaps).  Why not k_fwd_tc here: on 32 x 32 planes its
+// 128-row tile is four planes = 16 KB per ~60 MMAs and two hand-overs; measured 58 us for 35.7 MB (0.6 TB/s) at the cfg3 shape.
+// Measured at the cfg3 shape (8704 planes): 64 us against 58 - 82 us of k_fwd_tc -- latency-bound (issue slots 33 % busy, one
+// plane per warp at a time), not the FMA-pipe bound of (384 + 768) FFMA2 per plane; cfg3 gains 2.7 %.  Forcing four blocks
+// per SM (64 registers, spills) changed nothing.
+// Tables in shared memory: sT[w][ky] (pairs), sM[h][kx]; A goes through shared memory ([h][KL + 2] pairs per warp: the
+// lane changes from "row" to "kept row").
+// =============================================================================================
+template <int KL>
+__global__ void __launch_bounds__(256)
+k_fwd_plane32(const float* __restrict__ x, float2* __restrict__ spec, const float* __restrict__ tab, int npad,
+              const float2* __restrict__ M, long planes, int H, int W, int K0, int Kl, int layout) {
+  extern __shared__ float2 sm2[];
+  float2* sT = sm2;                                  // [32][KL]
+  float2* sM = sT + 32 * KL;                         // [32][32]
+  float2* sA = sM + 32 * 32;                         // [8 warps][32][KL + 2]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 32 * KL; i += 256) {
+    const int w = i / KL, ky = i - w * KL;
+    sT[i] = (w < W && ky < Kl) ? make_float2(__ldg(tab + (size_t)(2 * ky) * npad + w), __ldg(tab + (size_t)(2 * ky + 1) * npad + w))
+                               : make_float2(0.f, 0.f);
+  }
+  for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+    const int h = i >> 5, kx = i & 31;
+    sM[i] = (h < H && kx < K0) ? __ldg(M + (size_t)h * K0 + kx) : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  float2* myA = sA + (size_t)warp * 32 * (KL + 2);
+  for (long p0 = (long)blockIdx.x * 8; p0 < planes; p0 += (long)gridDim.x * 8) {
+    const long plane = p0 + warp;
+    const bool live = plane < planes;
+    // ---- stage 1 ----
+    float xr[32];
+#pragma unroll
+    for (int w = 0; w < 32; w++) xr[w] = 0.f;
+    if (live && lane < H) {
+      const float4* row = reinterpret_cast<const float4*>(x + ((size_t)plane * H + lane) * W);
+#pragma unroll
+      for (int w4 = 0; w4 < 8; w4++)
+        if (w4 * 4 < W) {
+          const float4 v = __ldg(row + w4);
+          xr[4 * w4] = v.x; xr[4 * w4 + 1] = v.y; xr[4 * w4 + 2] = v.z; xr[4 * w4 + 3] = v.w;
+        }
+    }
+    float2 acc[KL];
+#pragma unroll
+    for (int k = 0; k < KL; k++) acc[k] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < 32; w++) {
+      if (w < W) {
+        const float2 xx = make_float2(xr[w], xr[w]);
+#pragma unroll
+        for (int k = 0; k < KL; k += 2) {
+          const float4 t = *reinterpret_cast<const float4*>(sT + w * KL + k);
+          acc[k] = __ffma2_rn(xx, make_float2(t.x, t.y), acc[k]);
+          acc[k + 1] = __ffma2_rn(xx, make_float2(t.z, t.w), acc[k + 1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KL; k++) myA[lane * (KL + 2) + k] = acc[k];
+    __syncwarp();
+    // ---- stage 2 ----
+    float2 pr[KL], pi[KL];
+#pragma unroll
+    for (int k = 0; k < KL; k++) { pr[k] = make_float2(0.f, 0.f); pi[k] = make_float2(0.f, 0.f); }
+    for (int h = 0; h < H; h++) {
+      const float2 m = sM[h * 32 + lane];
+      const float2 mr = make_float2(m.x, m.x), mi = make_float2(m.y, m.y);
+#pragma unroll
+      for (int k = 0; k < KL; k += 2) {
+        const float4 a = *reinterpret_cast<const float4*>(myA + h * (KL + 2) + k);
+        pr[k] = __ffma2_rn(mr, make_float2(a.x, a.y), pr[k]);
+        pi[k] = __ffma2_rn(mi, make_float2(a.x, a.y), pi[k]);
+        pr[k + 1] = __ffma2_rn(mr, make_float2(a.z, a.w), pr[k + 1]);
+        pi[k + 1] = __ffma2_rn(mi, make_float2(a.z, a.w), pi[k + 1]);
+      }
+    }
+    // (m.re + i m.im)(a.re + i a.im) = (m.re a.re - m.im a.im) + i (m.re a.im + m.im a.re)
+    if (layout == 0) {
+      if (live && lane < K0) {
+        float2* dst = spec + ((size_t)plane * K0 + lane) * Kl;
+#pragma unroll
+        for (int k = 0; k < KL; k++)
+          if (k < Kl) dst[k] = make_float2(pr[k].x - pi[k].y, pr[k].y + pi[k].x);
+      }
+      __syncwarp();
+    } else {
+      // mode-major: the 8 planes of a block are consecutive, so the eight 8-byte stores of a mode (one per warp) fall into
+      // two 32-byte sectors and merge in L2
+      if (live && lane < K0) {
+        float2* dst = spec + (size_t)lane * Kl * planes + plane;
+#pragma unroll
+        for (int k = 0; k < KL; k++)
+          if (k < Kl) dst[(size_t)k * planes] = make_float2(pr[k].x - pi[k].y, pr[k].y + pi[k].x);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+static int launch_fwd_plane32(const b2no_plan* p, int which, const float* x, float* spec, long planes, cudaStream_t st) {
+  const int32_t* n = which == 0 ? p->g.nin : p->g.nout;
+  const int H = n[0], W = n[1], K0 = p->K[0], Kl = p->K[1];
+  const float* tab = which == 0 ? p->t_in : p->t_out;
+  const int npad = which == 0 ? p->npad_in : p->npad_out;
+  const float2* M = which == 0 ? p->m_fwd[0] : p->m_adjinv[0];
+  const int KL = Kl <= 8 ? 8 : (Kl <= 12 ? 12 : 16);
+  const size_t smem = sizeof(float2) * ((size_t)32 * KL + 32 * 32 + (size_t)8 * 32 * (KL + 2));
+  long blocks = (planes + 7) / 8;
+  const long cap = (long)b2no_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+#define FP32_LAUNCH(K)                                                                                                      \
+  do {                                                                                                                      \
+    if (smem > 48 * 1024) B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_fwd_plane32<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_fwd_plane32<K><<<(unsigned)blocks, 256, smem, st>>>(x, (float2*)spec, tab, npad, M, planes, H, W, K0, Kl, p->g.spec_layout); \
+  } while (0)
+  if (KL == 8) FP32_LAUNCH(8); else if (KL == 12) FP32_LAUNCH(12); else FP32_LAUNCH(16);
+#undef FP32_LAUNCH
+  B2NO_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================
 // forward pipeline
 // =============================================================================================
 extern "C" int b2no_dft_forward(const b2no_plan* p, int which, const float* x, float* spec, float* work,
@@ -329,6 +458,11 @@ extern "C" int b2no_dft_forward(const b2no_plan* p, int which, const float* x, f
   const int Kl = p->K[d - 1];
   if (d == 1) return run_r2c(p, which, x, spec, bc, st);
   if (d == 2) {
+    // small planes (RNO 32 x 32): one warp per plane on the FMA pipe -- the 128-row tensor-core tile is four planes there
+    B2NO_ENV_ONCE(env_small, "B2NO_FWD_SMALL", 1);
+    if (env_small && n[0] <= 32 && n[1] <= 32 && n[1] % 4 == 0 && p->K[0] <= 32 && Kl <= 16 && (((uintptr_t)x) & 15) == 0 &&
+        (p->g.spec_layout == 0 || p->g.spec_layout == 1))
+      return launch_fwd_plane32(p, which, x, spec, (long)bc, st);
     // tensor-core path (tc_dft.cu): one kernel, no intermediate, when the plane shape fits the 128-row tile
     const int rc = b2no_tc_dft_forward(p, which, x, spec, (long)bc, st);
     if (rc != 1) return rc;

@@ -820,17 +820,22 @@ def test_rno_layer_regrouped_vs_reference_composition():
 
 
 def test_dft_forward_runs_on_tensor_cores_at_bench_shapes():
-    """Launch evidence: at the cfg2 and cfg3 plane shapes b2no_dft_forward must take the tcgen05 kernel (k_fwd_tc), not its
-    CUDA-core stages -- a silent fallback would pass every numeric test at several times the cost."""
+    """Launch evidence: at the cfg2 plane shape b2no_dft_forward must take the tcgen05 kernel (k_fwd_tc), at the cfg3 shape
+    (32 x 32 planes) the one-launch warp-per-plane kernel, never the two CUDA-core stages -- a silent fallback would pass every
+    numeric test at several times the cost."""
     from pde_policylearning_b200 import ops
     dev = _dev()
     for grid, half, norm, C in (((128, 128), (6, 6), "forward", 32), ((32, 32), (12, 12), "ortho", 34)):
         plan = ops.get_plan(ops.SpecGeom(nin=grid, half=half, norm=norm), dev)
         x = torch.randn(4, C, *grid, device=dev)
         for which in (0, 1):
-            n0 = ops.tensor_core_launches()
+            n0, l0 = ops.tensor_core_launches(), ops.launch_count()
             ops.dft_forward(plan, which, x)
-            assert ops.tensor_core_launches() == n0 + 1, (grid, which)
+            if grid == (32, 32):
+                # small planes: ONE launch of the warp-per-plane kernel (k_fwd_plane32), not the two CUDA-core stages
+                assert ops.tensor_core_launches() == n0 and ops.launch_count() == l0 + 1, (grid, which)
+            else:
+                assert ops.tensor_core_launches() == n0 + 1, (grid, which)
         spec = torch.randn(4, C, *plan.kept, dtype=torch.cfloat, device=dev)
         w = torch.randn(C, C, device=dev)
         n0 = ops.tensor_core_launches()
