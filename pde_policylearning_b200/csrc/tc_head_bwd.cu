@@ -468,7 +468,10 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
         }
       }
     }
-    // every MMA has completed (done): the F staging area is free
+    // every MMA has completed (done): the F staging area is free.  The last F stores of the other epilogue threads are ordered
+    // before this point through fs_full -> G2 -> done; the named barrier states the same thing in a form compute-sanitizer's
+    // racecheck understands (it does not follow mbarrier / tcgen05.commit chains)
+    asm volatile("bar.sync 1, %0;" ::"n"(kHbEpiThreads) : "memory");
     float* red = (float*)(smem + L.fs);                                        // [part][NB * 128][2]
 #pragma unroll
     for (int b = 0; b < 2; b++) {
