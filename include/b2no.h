@@ -173,8 +173,9 @@ int b2no_mlp_head_bwd(const float* x, const float* w1, const float* b1, const fl
                       int b1_per_sample, int act, const float* dact_z, int dact, void* stream);
 /* WHOLE backward of the fused head in one kernel (same reference lines; replaces b2no_mlp_head_bwd + b2no_pw_wgrad on the
  * hidden-channel gradient): f is recomputed on the tensor cores and never written to memory.
- *   gx[b,i,p] as above;  grads = [ dW1 (hidden x ci) | db1 (hidden) | dw2 (hidden) ] contiguous floats:
- *   dW1[j,i] = sum_{b,p} f[b,j,p] x[b,i,p];  db1[j] = sum_{b,p} f[b,j,p];  dw2[j] = sum_{b,p} g[b,p] act(z1[b,j,p]).
+ *   gx[b,i,p] as above;  grads = [ dW1 (hidden x ci) | db1 (hidden) | dw2 (hidden) | db2 (1) ] contiguous floats:
+ *   dW1[j,i] = sum_{b,p} f[b,j,p] x[b,i,p];  db1[j] = sum_{b,p} f[b,j,p];  dw2[j] = sum_{b,p} g[b,p] act(z1[b,j,p]);
+ *   db2 = sum_{b,p} g[b,p].
  * b1 is (hidden) (a per-sample bias keeps the two-kernel path).  partial: b2no_mlp_head_bwd_fused_scratch_floats(ci, hidden)
  * floats.  Shapes: ci <= 32, hidden <= 256, pixels % 128 == 0 (b2no_mlp_head_bwd_fused_supported); otherwise
  * B2NO_E_UNSUPPORTED. */

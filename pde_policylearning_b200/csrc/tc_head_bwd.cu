@@ -3,7 +3,7 @@
 //   z1[j,p] = b1[j] + sum_c W1[j,c] x[c,p]                      (recomputed, never stored)
 //   f[j,p]  = g[p] w2[j] act'(z1[j,p])
 //   gx[c,p] = sum_j W1[j,c] f[j,p]   (* dact'(dz[c,p]) when given)
-//   dW1[j,c] = sum_p f[j,p] x[c,p],   db1[j] = sum_p f[j,p],   dw2[j] = sum_p g[p] act(z1[j,p])
+//   dW1[j,c] = sum_p f[j,p] x[c,p],   db1[j] = sum_p f[j,p],   dw2[j] = sum_p g[p] act(z1[j,p]),   db2 = sum_p g[p]
 //
 // Round 1 wrote f ("gz", batch x H x pixels fp32 = 1.07 GB at BASELINE config 2) to HBM for a separate weight-gradient
 // kernel.  Here f never leaves the SM.  Orientation: TMEM lane = hidden unit j (blocks of 128), column = pixel, so
@@ -42,7 +42,7 @@ struct HeadBwd {
   long P;
   const float* w1; const float* b1; const float* w2; const float* g; const float* dz;
   float* gx; float* partial;
-  int nsum;                                      // floats per partial row: H*Ci + 2H
+  int nsum;                                      // floats per partial row: H*Ci + 2H + 1
   int skip;                                      // ablation mask (B2NO_HB_SKIP, timing experiments only): 1 G1, 2 G3, 4 G2, 8 math, 16 gx stores, 32 Fs stores, 64 F TMEM stores
 };
 
@@ -375,6 +375,7 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
       dw2a[b] = make_float2(0.f, 0.f);
       dsa[b] = make_float2(0.f, 0.f);
     }
+    float2 gsum = make_float2(0.f, 0.f);          // sum of this thread's 16 g columns over the steps of hidden block 0 (-> db2)
     const uint32_t fs_base = smem_u32(smem) + L.fs + (uint32_t)(2 * part) * kHbSbo + (uint32_t)(jl >> 2) * kHbLbo + (uint32_t)(jl & 3) * 4;
     int it = 0;
     long n = 0;
@@ -393,6 +394,10 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
         tc_fence_before();
         warp_arrive(d1_empty);
         if (warp == 6) HB_STAMP(1, n, 1);
+        if (b == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) gsum = __fadd2_rn(gsum, make_float2(gv[i], gv[i + 1]));
+        }
         const float b1j = b == 0 ? b1r[0] : b1r[1], w2j = b == 0 ? w2r[0] : w2r[1];
         float2 dw2v = b == 0 ? dw2a[0] : dw2a[1], dsv = b == 0 ? dsa[0] : dsa[1];
         if (p.skip & 8) {
@@ -481,7 +486,10 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
         red[((size_t)part * NB * 128 + j) * 2 + 1] = (dsa[b].x + dsa[b].y) * w2r[b];
       }
     }
+    float* redg = red + (size_t)4 * NB * 128 * 2;                               // [part]: sum of g over this CTA's pixels
+    if (jl == 0) redg[part] = gsum.x + gsum.y;
     asm volatile("bar.sync 1, %0;" ::"n"(kHbEpiThreads) : "memory");
+    if (part == 0 && jl == 0) row[(size_t)p.H * p.Ci + 2 * p.H] = (redg[0] + redg[1]) + (redg[2] + redg[3]);   // db2
     if (part == 0) {
       for (int b = 0; b < NB; b++) {
         const int j = b * 128 + jl;
@@ -555,7 +563,7 @@ extern "C" int b2no_mlp_head_bwd_fused_supported(int ci, int hidden, int64_t pix
 
 extern "C" int64_t b2no_mlp_head_bwd_fused_scratch_floats(int ci, int hidden) {
   if (ci < 1 || hidden < 1) return B2NO_E_ARG;
-  return (int64_t)b2no_sm_count() * ((int64_t)hidden * ci + 2 * hidden);
+  return (int64_t)b2no_sm_count() * ((int64_t)hidden * ci + 2 * hidden + 1);
 }
 
 extern "C" int b2no_mlp_head_bwd_fused(const float* x, const float* w1, const float* b1, const float* w2, const float* g,
@@ -575,7 +583,7 @@ extern "C" int b2no_mlp_head_bwd_fused(const float* x, const float* w1, const fl
   const long tiles = (long)batch * p.tiles_per_img;
   if (tiles >= (1L << 30)) return B2NO_E_UNSUPPORTED;
   p.tiles = (int)tiles;
-  p.nsum = hidden * ci + 2 * hidden;
+  p.nsum = hidden * ci + 2 * hidden + 1;
   B2NO_ENV_ONCE(hb_skip, "B2NO_HB_SKIP", 0);
   p.skip = hb_skip;
   int grid = p.tiles < b2no_sm_count() ? p.tiles : b2no_sm_count();

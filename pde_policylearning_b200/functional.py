@@ -307,8 +307,8 @@ class MlpHeadFn(torch.autograd.Function):
         if (not per_sample_b1 and g.data_ptr() % 16 == 0
                 and ops.mlp_head_bwd_fused_supported(x.shape[1], w1m.shape[0], math.prod(x.shape[2:]))):
             # one kernel: gx, dW1, db1, dw2 (csrc/tc_head_bwd.cu)
-            gx, dw1, db1, dw2 = ops.mlp_head_bwd_fused(x, w1m, b1c, w2v, g, ctx.act)
-            db2 = g.sum().reshape(ctx.shapes[3]) if need_b2 else None
+            gx, dw1, db1, dw2, db2 = ops.mlp_head_bwd_fused(x, w1m, b1c, w2v, g, ctx.act)
+            db2 = db2.reshape(ctx.shapes[3]) if need_b2 else None
             return (gx if need_x else None, dw1.reshape(ctx.shapes[0]) if need_w1 else None,
                     db1.reshape(ctx.shapes[1]) if (need_b1 and b1c is not None) else None,
                     dw2.reshape(ctx.shapes[2]) if need_w2 else None, db2, None)

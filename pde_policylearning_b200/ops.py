@@ -385,20 +385,20 @@ def mlp_head_bwd_fused_supported(ci: int, hidden: int, pixels: int) -> bool:
 
 def mlp_head_bwd_fused(x, w1, b1, w2, g, act="gelu", dact_z=None, dact=None):
     """Whole backward of the Ci -> hidden -> act -> 1 head in one kernel (csrc/tc_head_bwd.cu): returns
-    (gx, dW1 (hidden, ci), db1 (hidden), dw2 (hidden)); the hidden-channel gradient is never written to memory."""
+    (gx, dW1 (hidden, ci), db1 (hidden), dw2 (hidden), db2 (1)); the hidden-channel gradient is never written to memory."""
     B, ci = x.shape[:2]
     hidden = w1.shape[0]
     P = math.prod(x.shape[2:])
     L = _lib.lib()
     assert b1 is None or b1.dim() == 1
     gx = torch.empty_like(x)
-    grads = torch.empty((hidden * ci + 2 * hidden,), dtype=torch.float32, device=x.device)
+    grads = torch.empty((hidden * ci + 2 * hidden + 1,), dtype=torch.float32, device=x.device)
     partial = torch.empty(int(L.b2no_mlp_head_bwd_fused_scratch_floats(ci, hidden)), dtype=torch.float32, device=x.device)
     check(L.b2no_mlp_head_bwd_fused(_ptr(x), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(g), _ptr(gx), _ptr(grads), _ptr(partial),
                                     B, ci, hidden, P, ACT[act], _ptr(dact_z), ACT[dact] if dact_z is not None else 0,
                                     _stream()), "mlp_head_bwd_fused")
     n = hidden * ci
-    return gx, grads[:n].view(hidden, ci), grads[n:n + hidden], grads[n + hidden:]
+    return gx, grads[:n].view(hidden, ci), grads[n:n + hidden], grads[n + hidden:n + 2 * hidden], grads[n + 2 * hidden:]
 
 
 def rno_gate_fwd(z, z2, hh, h):

@@ -206,7 +206,7 @@ def mlp_head_bwd_fused_supported(ci, hidden, pixels):
 
 
 def mlp_head_bwd_fused(x, w1, b1, w2, g, act="gelu", dact_z=None, dact=None):
-    """Definition of b2no_mlp_head_bwd_fused (include/b2no.h): (gx, dW1, db1, dw2) of out = w2 . act(W1 x + b1)."""
+    """Definition of b2no_mlp_head_bwd_fused (include/b2no.h): (gx, dW1, db1, dw2, db2) of out = w2 . act(W1 x + b1)."""
     nd = x.dim() - 2
     xd, w1d, w2d = (t.detach().to(RD).requires_grad_(True) for t in (x, w1, w2))
     b1d = (torch.zeros(w1.shape[0], dtype=RD) if b1 is None else b1.detach().to(RD)).requires_grad_(True)
@@ -219,7 +219,7 @@ def mlp_head_bwd_fused(x, w1, b1, w2, g, act="gelu", dact_z=None, dact=None):
         with torch.enable_grad():
             (da,) = torch.autograd.grad(_act(zz, dact).sum(), zz)
         gx = gx * da
-    return tuple(t.to(torch.float32) for t in (gx, dw1, db1, dw2))
+    return tuple(t.to(torch.float32) for t in (gx, dw1, db1, dw2, g.to(RD).sum().reshape(1)))
 
 
 def mlp_head_fwd(x, w1, b1, w2, b2, act="gelu"):

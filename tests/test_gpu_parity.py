@@ -539,9 +539,10 @@ def test_head_backward_one_kernel(case):
         zd = dz.double().requires_grad_(True)
         gx64 = gx64 * torch.autograd.grad(torch.nn.functional.gelu(zd).sum(), zd)[0]
     n0 = ops.tensor_core_launches()
-    gx, dw1, db1, dw2 = ops.mlp_head_bwd_fused(x, w1, b1, w2, g, act, dact_z=dz, dact="gelu" if with_dact else None)
+    gx, dw1, db1, dw2, db2 = ops.mlp_head_bwd_fused(x, w1, b1, w2, g, act, dact_z=dz, dact="gelu" if with_dact else None)
     assert ops.tensor_core_launches() == n0 + 1
-    errs = dict(gx=rel(gx, gx64), dw1=rel(dw1, dw164), db1=rel(db1, db164), dw2=rel(dw2, dw264))
+    errs = dict(gx=rel(gx, gx64), dw1=rel(dw1, dw164), db1=rel(db1, db164), dw2=rel(dw2, dw264),
+                db2=abs(float(db2) - float(g.double().sum())) / float(g.double().abs().sum()))
     print("head backward (one kernel)", case, {k: f"{v:.2e}" for k, v in errs.items()})
     for k, v in errs.items():
         assert v < 2e-5, (k, v)
