@@ -537,12 +537,12 @@ def run_b200(args):
     # resident inputs: the graph's static buffers already hold this rank's batch -> no copies in the timed region
     res_in = (graphed.static_in[0], graphed.static_tgt) if graphed is not None else (p_dev, t_dev)
     # clock / power pre-warm (untimed, not part of W): a GPU that sat idle through the host-side set-up measured its first
-    # 20 steps 9 % slow (2.61 vs 2.38 ms, profiles/r02_l) -- run the step for ~0.3 s before the W warm-up steps
-    t_pre = time.perf_counter()
-    while time.perf_counter() - t_pre < 0.3:
-        for _ in range(10):
-            step(*res_in)
-        torch.cuda.synchronize()
+    # 20 steps 9 % slow (2.61 vs 2.38 ms, profiles/r02_l) -- run the step ~0.3 s worth of times before the W warm-up steps
+    # A FIXED number of steps: the step contains the gradient all-reduce at N > 1, so every rank must run the same count
+    # (a time-based loop let the ranks drift apart and deadlocked / crawled at N = 8)
+    for _ in range(120):
+        step(*res_in)
+    torch.cuda.synchronize()
     for _ in range(args.warmup):
         step(*res_in)
     l0 = ops.launch_count()
