@@ -629,6 +629,7 @@ def run_b200(args):
         cpu = cpu_reference_run(steps=20, warmup=2, sample_batch=16) if world == 1 else None   # ~10 s of host work
         cfg = config_dict(world)
         cfg["cuda_graph"] = graphed is not None
+        cfg["prewarm_steps"] = 120          # untimed, before the W warm-up steps (fixed count: same on every rank)
         cfg["optimizer"] = "fused flat Adam (lr 1e-3, weight_decay 1e-4), inside the timed step"
         cfg["grad_allreduce"] = ("none (1 GPU)" if world == 1 else
                                  ("per-bucket NCCL all-reduce launched from gradient hooks during backward (B2NO_OVERLAP_AR=1)"
