@@ -222,3 +222,12 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+
+
+def test_bench_warmup_runs_a_fixed_number_of_steps():
+    """The training step contains the gradient all-reduce at N > 1, so every untimed step before the timed region must be
+    counted, not clocked: a time-based warm-up loop gave the ranks different numbers of collectives and the 8-GPU run hung."""
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    region = src[src.index("res_in = (graphed.static_in[0]"):src.index("l0 = ops.launch_count()")]
+    assert "step(*res_in)" in region
+    assert "perf_counter" not in region and "time.time" not in region and "while " not in region
