@@ -71,7 +71,7 @@ __device__ __forceinline__ void warp_arrive2(uint64_t* bar_a, uint64_t* bar_b) {
   if ((threadIdx.x & 31) == 0) { mbar_arrive(bar_a); mbar_arrive(bar_b); }
 }
 
-struct HbLayout { uint32_t fs, fs_img, wt, xt, xt_img, xk, raw, g, bars, total; };
+struct HbLayout { uint32_t fs, fs_img, wt, xt, xt_img, xk, raw, g, gxb, bars, total; };
 
 __host__ __device__ inline HbLayout hb_layout(int Cq, int Hp) {
   HbLayout L;
@@ -82,6 +82,7 @@ __host__ __device__ inline HbLayout hb_layout(int Cq, int Hp) {
   L.xk = o; o += (uint32_t)(2 * Cq / 8) * kHbSbo;
   L.raw = o; o += (uint32_t)Cq * 512;
   L.g = o; o += 3 * 512;
+  L.gxb = o; o += 64 * 16 * 4;                                     // gx epilogue: [16 channels][64 px] staging of the TMA store
   L.bars = o; o += 8 * 13 + 16;
   L.total = o + 1024;
   return L;
@@ -91,7 +92,7 @@ __host__ __device__ inline uint32_t hb_tmem_cols(int Cq, int NB) { return (uint3
 
 template <bool GELU, int CQ>
 __global__ void __launch_bounds__(kHbThreads, 1)
-k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
+k_head_bwd(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmg, const HeadBwd p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr int Cq = CQ;                     // channels rounded up to 16 (compile time: the MMA issue loops unroll)
@@ -132,7 +133,7 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
   }
   fence_proxy_async();
   if (warp == 1) tmem_alloc(tslot, ncols);
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmx);
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmx); tma_prefetch_desc(&tmg); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -284,6 +285,10 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
     // columns [0,Cq) + [Cq,2Cq) = channels
     const int quad = warp & 3;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    // The chunk leaves as TMA stores of [16 channels x 64 px] boxes from a 4 KB staging buffer (issued by one thread, asynchronous):
+    // 32 per-channel 64-byte global stores per warp kept these warps busy for ~1500 cycles per chunk and delayed the X images
+    // of the next tile (60 us of the kernel).
+    const uint32_t gxb = sb + L.gxb;
     auto gx_epilogue = [&](long qc, int tile_of, int q) {
       mbar_wait(d2_full, (uint32_t)qc & 1u);
       tc_fence_after();
@@ -299,20 +304,28 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
       }
       tc_fence_before();
       warp_arrive(d2_empty);
-      if (lane < 16 && !(p.skip & 16)) {
-        const int bimg = tile_of / p.tiles_per_img;
-        const long px = (long)(tile_of - bimg * p.tiles_per_img) * 128 + q * 64 + quad * 16 + lane;
-        const size_t o0 = (size_t)bimg * p.Ci * p.P + (size_t)px;
-        float* gp = p.gx + o0;
-        if (p.dz) {
-          const float* zp = p.dz + o0;
+      const int bimg = tile_of / p.tiles_per_img;
+      const int pxc = (tile_of - bimg * p.tiles_per_img) * 128 + q * 64;        // first pixel of the chunk inside its image
+      const int pl = quad * 16 + lane;                                          // pixel of the chunk (lanes 0..15 hold rows)
+      if (p.dz && lane < 16) {
+        const float* zp = p.dz + (size_t)bimg * p.Ci * p.P + (size_t)(pxc + pl);
 #pragma unroll
-          for (int c = 0; c < Cq; c++)
-            if (c < p.Ci) gp[(size_t)c * p.P] = r[c] * hb_act_grad(__ldg(zp + (size_t)c * p.P), p.dact);
-        } else {
+        for (int c = 0; c < Cq; c++)
+          if (c < p.Ci) r[c] *= hb_act_grad(__ldg(zp + (size_t)c * p.P), p.dact);
+      }
 #pragma unroll
-          for (int c = 0; c < Cq; c++)
-            if (c < p.Ci) gp[(size_t)c * p.P] = r[c];
+      for (int c0 = 0; c0 < Cq; c0 += 16) {
+        if (warp == 2 && lane == 0) tma_store_wait_read();                      // the staging buffer is free again
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (lane < 16) {
+#pragma unroll
+          for (int i = 0; i < 16; i++) sts_f32(gxb + (uint32_t)(i * 64 + pl) * 4u, r[c0 + i]);
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (warp == 2 && lane == 0 && !(p.skip & 16)) {
+          tma_store_3d(&tmg, smem + L.gxb, pxc, c0, bimg);                      // channels >= Ci are clipped by the tensor map
+          tma_store_commit();
         }
       }
     };
@@ -359,6 +372,7 @@ k_head_bwd(const __grid_constant__ CUtensorMap tmx, const HeadBwd p) {
       gx_epilogue((long)it * cpt, tile, 0);
     }
     if (it > 0) gx_epilogue((long)it * cpt - 1, t_end - 1, cpt - 1);
+    if (warp == 2 && lane == 0) tma_store_wait_all();
   } else {
     // ===================== epilogue: 4 lane quadrants (hidden units) x 4 column parts (16 pixels of the chunk) =====================
     const int part = (warp - 6) >> 2;
@@ -595,10 +609,13 @@ extern "C" int b2no_mlp_head_bwd_fused(const float* x, const float* w1, const fl
   uint64_t str[3] = {4, (uint64_t)pixels * 4, (uint64_t)pixels * 4 * ci};
   uint32_t box[3] = {128, (uint32_t)p.Cq, 1};
   if (make_tmap_f32(&tmx, x, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return B2NO_E_UNSUPPORTED;
+  CUtensorMap tmg;
+  uint32_t gbox[3] = {64, 16, 1};
+  if (((uintptr_t)gx & 15) || make_tmap_f32(&tmg, gx, 3, dims, str, gbox, CU_TENSOR_MAP_SWIZZLE_NONE)) return B2NO_E_UNSUPPORTED;
 #define HB_LAUNCH(G, C)                                                                                                   \
   do {                                                                                                                   \
     B2NO_CHECK_CUDA(cudaFuncSetAttribute(k_head_bwd<G, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total)); \
-    k_head_bwd<G, C><<<(unsigned)grid, kHbThreads, L.total, st>>>(tmx, p);                                              \
+    k_head_bwd<G, C><<<(unsigned)grid, kHbThreads, L.total, st>>>(tmx, tmg, p);                                              \
   } while (0)
   const bool gelu = act == B2NO_ACT_GELU;
   if (p.Cq == 32) { if (gelu) HB_LAUNCH(true, 32); else HB_LAUNCH(false, 32); }
