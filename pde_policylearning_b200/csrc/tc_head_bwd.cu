@@ -17,10 +17,13 @@
 //   G3 (TS): D3[b][128 j x 2C] += F (TMEM) x XK chunk [(x hi ; x lo) x 64 px]   (cols [0,C): f x_hi, [C,2C): f_hi x_lo)
 //   G2 (SS, M = 64): D2[64 px x 2C] += Fs (smem) x WT block [(W1^T hi ; W1^T lo) x 128 j]; after the last block: gx epilogue
 // Everything is single buffered (TMEM: W1 4 NB C + D1 64 + F 128 + D3 2 NB C + D2 2C = 512 columns at C = 32, H = 256;
-// shared memory 222 KB): the tensor pipe is the bound (~2400 cycles per step against ~1500 of epilogue math), so the
-// epilogue warps wait for the pipe, not the other way round.
-// Warp roles: 0 TMA producer, 1 MMA issuer, 2-5 X converter (thread = pixel) + gx epilogue (D2 -> global), 6-21 epilogue
-// (4 lane quadrants x 4 column parts of 16 pixels).
+// shared memory 226 KB of 227): the steps are a hand-over chain  F(n) visible -> G3 / G2(n) -> F(n + 1) may be written.
+// Measured (B200, cfg2 shape, 429 us; DESIGN.md section 4, profiles/r02_l ... r02_p): step period ~4000 cycles = FMA-pipe math
+// ~1800 + TMEM read / F write ~1000 + barrier round trips; the tensor pipe is ~40 % busy.  F has two hand-overs: the TMEM copy is
+// released by G3 (ft_*), the shared-memory copy by G2 (fs_*).
+// Warp roles: 0 TMA producer (x tile + g tile), 1 MMA issuer, 2-5 X converter (thread = pixel: raw tile -> XT, XK images, hi / lo)
+// which also drain the gx accumulator (D2 -> 4 KB staging -> TMA store, off the chain), 6-21 epilogue (4 lane quadrants x 4
+// column parts of 16 pixels).
 #include <string.h>
 
 #include "common.cuh"
